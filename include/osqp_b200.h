@@ -1,0 +1,57 @@
+/*
+ * osqp_b200.h -- engine-specific extensions exported by osqp.jl_b200/lib/libosqp.so next to
+ * the 30 reference symbols of osqp.h.  Nothing in the reference calls these; they exist for
+ * measurement (bench.py, profiles/), for tuning the inner solver, and for the batched path
+ * that the reference has no API for (BASELINE.json config 5, SURVEY.md 8b "Batch extension").
+ */
+#ifndef OSQP_B200_EXT_H
+#define OSQP_B200_EXT_H
+#include "osqp.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct {
+  c_int   device;        /* CUDA device ordinal the workspace lives on */
+  c_int   grid;          /* persistent-kernel grid (blocks) */
+  c_int   block;         /* threads per block */
+  c_int   lanes_A;       /* threads cooperating on one row of A */
+  c_int   lanes_N;       /* threads cooperating on one row of P / A' */
+  c_int   nnz_A;         /* stored non-zeros of A */
+  c_int   nnz_P_full;    /* stored non-zeros of the full symmetric P */
+  c_int   launches;      /* kernels launched for this workspace since setup */
+  c_int   admm_iters;    /* last solve: ADMM iterations executed */
+  c_int   pcg_iters;     /* last solve: total PCG iterations */
+  c_int   info_evals;    /* last solve: residual/termination evaluations */
+  c_int   refreshes;     /* last solve: full residual rebuilds */
+  c_float kernel_ms;     /* last solve: CUDA-event duration of the admm_kernel launch */
+  c_float polish_ms;     /* last solve: CUDA-event duration of the polish_kernel launch (0 if none) */
+  c_float alg_bytes;     /* last solve: algorithmic bytes of the admm_kernel launch (DESIGN.md model) */
+  c_float spmv_bytes_A;  /* algorithmic bytes of one A v, A'w, (P+sigma I)v  (12 B/nnz CSR model) */
+  c_float spmv_bytes_At;
+  c_float spmv_bytes_P;
+} OSQPB200Profile;
+
+/* Measurement of the last osqp_solve on this workspace. */
+c_int osqp_b200_get_profile(const OSQPWorkspace *work, OSQPB200Profile *out);
+
+/* Inner-solver controls: ||r||inf <= max(rel_tol*||b||inf, abs_tol); values <= 0 keep the current one.
+ * refresh_every: rebuild z~ = A x~ and r = b - K x~ from scratch every k ADMM iterations (0: only when needed). */
+c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float rel_tol, c_float abs_tol, c_int max_iter, c_int refresh_every);
+
+/* Standalone SpMV with the resident (scaled) matrices, same device code and work split as the ADMM
+ * kernel.  which: 0 out=A in | 1 out=A' in | 2 out=(P+sigma I) in.  Host buffers; runs `reps`
+ * launches and returns the mean CUDA-event time per launch in *ms_per_rep. */
+c_int osqp_b200_spmv(OSQPWorkspace *work, c_int which, const c_float *in_host, c_float *out_host, c_int reps,
+                     c_float *ms_per_rep);
+
+/* Scaling computed at setup: D (n), E (m), c -- for parity checks against the oracle. */
+c_int osqp_b200_get_scaling(OSQPWorkspace *work, c_float *D, c_float *E, c_float *c);
+
+c_int osqp_b200_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,1245 @@
+// kernels.cu -- hand-written sm_100a kernels of the B200 OSQP engine.
+//
+// One osqp_solve = ONE persistent cooperative launch (admm_kernel): the whole ADMM loop of
+// libosqp 0.6.2 runs on the device -- reduced-KKT Jacobi-PCG
+// built on CSR SpMV with A, A' and P+sigma I, fused with the [l,u] projection, the dual update,
+// the infinity-norm residuals, termination / infeasibility tests and adaptive rho.  Phases are
+// separated by a hand-written grid barrier; dot products and norms ride on the same barrier
+// through a fixed-order (deterministic) two-level reduction.  Nothing here is a dense
+// contraction, so tensor cores are not used: the roofline is HBM.
+//
+// Work split: block b owns a contiguous, nnz-balanced range of rows of A (m-range) and of
+// P / A' (n-range); all element-wise vector work on an index is done by the block owning it.
+#include "engine.cuh"
+
+#include <cooperative_groups.h>
+#include <math.h>
+
+namespace osqpb200 {
+
+namespace {
+
+constexpr double kInfty = 1e30;
+constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
+constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
+constexpr double kDivisionTol = 1e-30;
+constexpr int kPrintInterval = 200;
+
+constexpr long long ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4, ST_MAX_ITER = -2,
+                    ST_PINF = -3, ST_DINF = -4, ST_TIME_LIMIT = -6, ST_NON_CVX = -7, ST_UNSOLVED = -10;
+
+// ------------------------------------------------------------------ memory helpers
+// Matrix streams are read once per phase and never written inside a launch: non-coherent path,
+// no L1 allocation, so L1 stays free for the gathered dense vector.
+__device__ __forceinline__ double ld_stream(const double *p) {
+  double v;
+  asm("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int *p) {
+  int v;
+  asm("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ------------------------------------------------------------------ grid barrier + reductions
+struct Grid {
+  unsigned *count, *gen;
+  unsigned nblocks, local_gen;
+  int bank;
+  double *red;
+};
+
+__device__ __forceinline__ void grid_init(Grid &g, const DevPtrs &d) {
+  g.count = d.bar;
+  g.gen = d.bar + 1;
+  g.nblocks = gridDim.x;
+  g.local_gen = ld_acquire(g.gen);  // nobody can advance it before every block has arrived once
+  g.bank = 0;
+  g.red = d.red;
+}
+
+__device__ __forceinline__ void grid_barrier(Grid &g) {
+  __syncthreads();
+  if (g.nblocks > 1) {
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned arrived = atomicAdd(g.count, 1u);
+      if (arrived == g.nblocks - 1) {
+        atomicExch(g.count, 0u);
+        __threadfence();
+        atomicAdd(g.gen, 1u);
+      } else {
+        while (ld_acquire(g.gen) == g.local_gen) {
+        }
+      }
+      __threadfence();
+    }
+    g.local_gen++;
+    __syncthreads();
+  }
+}
+
+// op mask bit k = 1: slot k is a max-reduction, else a sum.
+struct RedSmem {
+  double part[32][kRedSlots];
+  double res[kRedSlots];
+};
+
+template <int NV>
+__device__ __forceinline__ void reduce_and_barrier(Grid &g, RedSmem &sm, double (&v)[NV], unsigned maxmask) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double a = v[k];
+    if (maxmask & (1u << k)) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    } else {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    if (lane == 0) sm.part[warp][k] = a;
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    const int k = threadIdx.x;
+    double a = sm.part[0][k];
+    if (maxmask & (1u << k)) {
+      for (int w = 1; w < nwarps; w++) a = fmax(a, sm.part[w][k]);
+    } else {
+      for (int w = 1; w < nwarps; w++) a += sm.part[w][k];
+    }
+    if (g.nblocks > 1) g.red[((size_t)g.bank * kRedSlots + k) * g.nblocks + blockIdx.x] = a;
+    else sm.res[k] = a;
+  }
+  grid_barrier(g);
+  if (g.nblocks > 1) {
+    for (int k = warp; k < NV; k += nwarps) {
+      const double *src = g.red + ((size_t)g.bank * kRedSlots + k) * g.nblocks;
+      const bool ismax = maxmask & (1u << k);
+      double a = ismax ? -INFINITY : 0.0;
+      for (unsigned i = lane; i < g.nblocks; i += 32) {
+        double x = __ldcg(src + i);
+        a = ismax ? fmax(a, x) : a + x;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        double x = __shfl_xor_sync(0xffffffffu, a, o);
+        a = ismax ? fmax(a, x) : a + x;
+      }
+      if (lane == 0) sm.res[k] = a;
+    }
+    g.bank ^= 1;
+    __syncthreads();
+  }
+#pragma unroll
+  for (int k = 0; k < NV; k++) v[k] = sm.res[k];
+  __syncthreads();  // sm.res may be rewritten by the next reduction
+}
+
+// ------------------------------------------------------------------ row-parallel SpMV building block
+// `lanes` consecutive threads cooperate on one row (128-bit friendly: consecutive lanes read
+// consecutive (val, col) pairs -> fully coalesced 8 B + 4 B streams), partial sums are combined
+// with width-limited warp shuffles, and lane 0 of the group runs the epilogue.  The loop trip
+// count is uniform across the block so the shuffles are always convergent.
+template <int NV>
+struct Acc {
+  double a[NV];
+};
+
+template <int NV, typename Term>
+__device__ __forceinline__ void row_accumulate(const int *__restrict__ rowptr, const int *__restrict__ col,
+                                               const double *__restrict__ val, int row, bool valid, int sub, int lanes,
+                                               Acc<NV> &acc, Term term) {
+  int k0 = 0, k1 = 0;
+  if (valid) {
+    k0 = ld_stream(rowptr + row);
+    k1 = ld_stream(rowptr + row + 1);
+  }
+#pragma unroll 4
+  for (int k = k0 + sub; k < k1; k += lanes) {
+    const int c = ld_stream(col + k);
+    const double a = ld_stream(val + k);
+    term(acc, c, a);
+  }
+}
+
+template <int NV>
+__device__ __forceinline__ void group_reduce(Acc<NV> &acc, int lanes) {
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    double a = acc.a[v];
+    for (int o = lanes >> 1; o; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o, lanes);
+    acc.a[v] = a;
+  }
+}
+
+// ------------------------------------------------------------------ scaled/infeasibility info scalars
+struct InfoScalars {
+  double pri_t, pri_r, nz_t, nz_r, nAx_t, nAx_r, ndy_t, lhs, maxU_t, maxNegL_t;
+  double dua_t, dua_r, nq_t, nq_r, nAty_t, nAty_r, nPx_t, nPx_r, obj, ndx_t, qdx, nPdx_t, nAtdy_t;
+  double pri_res, dua_res, obj_val;  // what update_info publishes
+};
+
+// ------------------------------------------------------------------ PCG on K = P + sigma I + A' diag(rho) A
+// Chronopoulos-Gear single-reduction variant: 3 grid barriers per iteration
+// (after t = A u | after w = K u with delta = w.u | after the vector updates with gamma, |r|inf).
+// On entry: r, uu = Minv r are set on every n-range, gamma = r.uu and rn = |r|inf are reduced.
+// x (n) is advanced in place; if zvec != nullptr it is advanced with A p (z = A x recurrence).
+struct PcgVecs {
+  double *r, *uu, *p, *s, *w, *t, *tr, *Ap;
+};
+
+__device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, const DevPtrs &d, const PcgVecs &v, const double *rho_vec,
+                                    const double *Minv, double sigma, double *xvec, double *zvec, double gamma,
+                                    double rn, double thresh, int max_it, int m0, int m1, int n0, int n1) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lanesA = d.A.lanes, lanesN = d.At.lanes;
+  const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  double a_old = 1.0, gamma_old = 1.0;
+  int it = 0;
+  while (rn > thresh && it < max_it) {
+    // ---- phase A: t = A uu, tr = rho .* t
+    if (d.m > 0) {
+      for (int base = m0; base < m1; base += ngrpA) {
+        const int row = base + grpA;
+        const bool valid = row < m1;
+        Acc<1> acc;
+        acc.a[0] = 0.0;
+        row_accumulate<1>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * v.uu[c]; });
+        group_reduce<1>(acc, lanesA);
+        if (valid && subA == 0) {
+          v.t[row] = acc.a[0];
+          v.tr[row] = rho_vec[row] * acc.a[0];
+        }
+      }
+      grid_barrier(g);
+    }
+    // ---- phase B: w = P uu + sigma uu + A' tr ; delta = w . uu
+    double red1[1] = {0.0};
+    for (int base = n0; base < n1; base += ngrpN) {
+      const int row = base + grpN;
+      const bool valid = row < n1;
+      Acc<1> acc;
+      acc.a[0] = 0.0;
+      row_accumulate<1>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * v.uu[c]; });
+      if (d.m > 0)
+        row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * v.tr[c]; });
+      group_reduce<1>(acc, lanesN);
+      if (valid && subN == 0) {
+        const double uj = v.uu[row];
+        const double wj = acc.a[0] + sigma * uj;
+        v.w[row] = wj;
+        red1[0] += wj * uj;
+      }
+    }
+    reduce_and_barrier<1>(g, sm, red1, 0u);
+    const double delta = red1[0];
+    double beta, alpha;
+    if (it == 0) {
+      beta = 0.0;
+      alpha = gamma / delta;
+    } else {
+      beta = gamma / gamma_old;
+      alpha = gamma / (delta - beta * gamma / a_old);
+    }
+    if (!(alpha > 0.0) || !isfinite(alpha)) break;  // breakdown: p'Kp <= 0 or exact convergence
+    // ---- phase V: vector recurrences
+    double red2[2] = {0.0, 0.0};
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double uj = v.uu[j], wj = v.w[j];
+      const double pj = (it == 0) ? uj : uj + beta * v.p[j];
+      const double sj = (it == 0) ? wj : wj + beta * v.s[j];
+      v.p[j] = pj;
+      v.s[j] = sj;
+      xvec[j] += alpha * pj;
+      const double rj = v.r[j] - alpha * sj;
+      v.r[j] = rj;
+      const double un = Minv[j] * rj;
+      v.uu[j] = un;
+      red2[0] += rj * un;
+      red2[1] = fmax(red2[1], fabs(rj));
+    }
+    if (zvec != nullptr) {
+      for (int i = m0 + tid; i < m1; i += nth) {
+        const double api = (it == 0) ? v.t[i] : v.t[i] + beta * v.Ap[i];
+        v.Ap[i] = api;
+        zvec[i] += alpha * api;
+      }
+    }
+    reduce_and_barrier<2>(g, sm, red2, 0x2u);
+    gamma_old = gamma;
+    gamma = red2[0];
+    rn = red2[1];
+    a_old = alpha;
+    it++;
+  }
+  return it;
+}
+
+// ------------------------------------------------------------------ update_info (row a9) + infeasibility products (row a10)
+// One phase streams A, P and A' once each with two gathered vectors per matrix:
+//   A:(x, dx) -> Ax, A dx | P:(x, dx) -> Px, P dx | A':(y, dy) -> A'y, A'dy
+__device__ __noinline__ void compute_info(Grid &g, RedSmem &sm, const DevPtrs &d, const SolveCfg &c, double cost_c,
+                                          double cost_cinv, const double *xv, const double *zv, const double *yv,
+                                          int m0, int m1, int n0, int n1, InfoScalars &S) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const bool unscale = c.scaling && !c.scaled_termination;
+  const int lanesA = d.A.lanes, lanesN = d.At.lanes;
+  const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  double v[23];
+#pragma unroll
+  for (int k = 0; k < 23; k++) v[k] = 0.0;
+  v[8] = -INFINITY;
+  v[9] = -INFINITY;
+  // ---- m rows
+  for (int base = m0; base < m1; base += ngrpA) {
+    const int row = base + grpA;
+    const bool valid = row < m1;
+    Acc<2> acc;
+    acc.a[0] = acc.a[1] = 0.0;
+    row_accumulate<2>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc, [&](Acc<2> &ac, int cc, double a) {
+      ac.a[0] += a * xv[cc];
+      ac.a[1] += a * d.dx[cc];
+    });
+    group_reduce<2>(acc, lanesA);
+    if (valid && subA == 0) {
+      const double Ax = acc.a[0], Adx = acc.a[1];
+      const double zi = zv[row], ei = unscale ? d.Einv[row] : 1.0, Ei = unscale ? d.E[row] : 1.0;
+      const double li = d.l[row], ui = d.u[row], dyi = d.dy[row];
+      const double pr = fabs(Ax - zi);
+      v[0] = fmax(v[0], ei * pr);
+      v[1] = fmax(v[1], pr);
+      v[2] = fmax(v[2], ei * fabs(zi));
+      v[3] = fmax(v[3], fabs(zi));
+      v[4] = fmax(v[4], ei * fabs(Ax));
+      v[5] = fmax(v[5], fabs(Ax));
+      v[6] = fmax(v[6], Ei * fabs(dyi));
+      v[7] += ui * fmax(dyi, 0.0) + li * fmin(dyi, 0.0);
+      const double adx = ei * Adx;
+      if (ui < kInfty * kMinScaling) v[8] = fmax(v[8], adx);
+      if (li > -kInfty * kMinScaling) v[9] = fmax(v[9], -adx);
+    }
+  }
+  // ---- n rows
+  for (int base = n0; base < n1; base += ngrpN) {
+    const int row = base + grpN;
+    const bool valid = row < n1;
+    Acc<4> acc;
+    acc.a[0] = acc.a[1] = acc.a[2] = acc.a[3] = 0.0;
+    row_accumulate<4>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc, [&](Acc<4> &ac, int cc, double a) {
+      ac.a[0] += a * xv[cc];
+      ac.a[1] += a * d.dx[cc];
+    });
+    if (d.m > 0)
+      row_accumulate<4>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                        [&](Acc<4> &ac, int cc, double a) {
+                          ac.a[2] += a * yv[cc];
+                          ac.a[3] += a * d.dy[cc];
+                        });
+    group_reduce<4>(acc, lanesN);
+    if (valid && subN == 0) {
+      const double Px = acc.a[0], Pdx = acc.a[1], Aty = acc.a[2], Atdy = acc.a[3];
+      const double qj = d.q[row], xj = xv[row], dxj = d.dx[row];
+      const double di = unscale ? d.Dinv[row] : 1.0, Dj = unscale ? d.D[row] : 1.0;
+      const double dr = fabs(qj + Px + Aty);
+      v[10] = fmax(v[10], di * dr);
+      v[11] = fmax(v[11], dr);
+      v[12] = fmax(v[12], di * fabs(qj));
+      v[13] = fmax(v[13], fabs(qj));
+      v[14] = fmax(v[14], di * fabs(Aty));
+      v[15] = fmax(v[15], fabs(Aty));
+      v[16] = fmax(v[16], di * fabs(Px));
+      v[17] = fmax(v[17], fabs(Px));
+      v[18] += xj * (0.5 * Px + qj);
+      v[19] = fmax(v[19], Dj * fabs(dxj));
+      v[20] += qj * dxj;
+      v[21] = fmax(v[21], di * fabs(Pdx));
+      v[22] = fmax(v[22], di * fabs(Atdy));
+    }
+  }
+  // sums: 7 (lhs), 18 (obj), 20 (q'dx); everything else is a max
+  reduce_and_barrier<23>(g, sm, v, 0x7FFFFFu & ~((1u << 7) | (1u << 18) | (1u << 20)));
+  S.pri_t = v[0]; S.pri_r = v[1]; S.nz_t = v[2]; S.nz_r = v[3]; S.nAx_t = v[4]; S.nAx_r = v[5];
+  S.ndy_t = v[6]; S.lhs = v[7]; S.maxU_t = v[8]; S.maxNegL_t = v[9];
+  S.dua_t = v[10]; S.dua_r = v[11]; S.nq_t = v[12]; S.nq_r = v[13]; S.nAty_t = v[14]; S.nAty_r = v[15];
+  S.nPx_t = v[16]; S.nPx_r = v[17]; S.obj = v[18]; S.ndx_t = v[19]; S.qdx = v[20]; S.nPdx_t = v[21];
+  S.nAtdy_t = v[22];
+  S.obj_val = c.scaling ? S.obj * cost_cinv : S.obj;
+  S.pri_res = (d.m == 0) ? 0.0 : S.pri_t;
+  S.dua_res = unscale ? cost_cinv * S.dua_t : S.dua_t;
+}
+
+// check_termination of libosqp 0.6.2; returns the new status or ST_UNSOLVED.
+__device__ __forceinline__ long long check_termination(const InfoScalars &S, const SolveCfg &c, int m, double cost_c,
+                                                       double cost_cinv, bool approximate) {
+  double eps_abs = c.eps_abs, eps_rel = c.eps_rel, eps_pinf = c.eps_prim_inf, eps_dinf = c.eps_dual_inf;
+  if (S.pri_res > kInfty || S.dua_res > kInfty) return ST_NON_CVX;
+  if (approximate) {
+    eps_abs *= 10; eps_rel *= 10; eps_pinf *= 10; eps_dinf *= 10;
+  }
+  const bool unscale = c.scaling && !c.scaled_termination;
+  bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
+  if (m == 0) prim_ok = true;
+  else {
+    const double eps_prim = eps_abs + eps_rel * fmax(S.nz_t, S.nAx_t);
+    if (S.pri_res < eps_prim) prim_ok = true;
+    else if (S.ndy_t > kDivisionTol && S.lhs < -eps_pinf * S.ndy_t) prim_inf = S.nAtdy_t < eps_pinf * S.ndy_t;
+  }
+  double mx = fmax(S.nq_t, fmax(S.nAty_t, S.nPx_t));
+  if (unscale) mx *= cost_cinv;
+  const double eps_dual = eps_abs + eps_rel * mx;
+  if (S.dua_res < eps_dual) dual_ok = true;
+  else {
+    const double cs = unscale ? cost_c : 1.0;
+    if (S.ndx_t > kDivisionTol && S.qdx < -cs * eps_dinf * S.ndx_t && S.nPdx_t < cs * eps_dinf * S.ndx_t)
+      dual_inf = !(S.maxU_t > eps_dinf * S.ndx_t) && !(S.maxNegL_t > eps_dinf * S.ndx_t);
+  }
+  if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
+  if (prim_inf) return approximate ? ST_PINF_INACC : ST_PINF;
+  if (dual_inf) return approximate ? ST_DINF_INACC : ST_DINF;
+  return ST_UNSOLVED;
+}
+
+__device__ __forceinline__ double rho_estimate(const InfoScalars &S, double rho) {
+  double pri = S.pri_r / (fmax(S.nz_r, S.nAx_r) + 1e-10);
+  double dua = S.dua_r / (fmax(S.nq_r, fmax(S.nAty_r, S.nPx_r)) + 1e-10);
+  double est = rho * sqrt(pri / (dua + 1e-10));
+  return fmin(fmax(est, kRhoMin), kRhoMax);
+}
+
+// Minv = 1 / (P_jj + sigma + sum_i rho_i A_ij^2) on rows [n0, n1)
+__device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho_vec, double sigma, double *Minv,
+                                             int n0, int n1) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int lanesN = d.At.lanes;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  for (int base = n0; base < n1; base += ngrpN) {
+    const int row = base + grpN;
+    const bool valid = row < n1;
+    Acc<1> acc;
+    acc.a[0] = 0.0;
+    if (d.m > 0)
+      row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += rho_vec[c] * a * a; });
+    group_reduce<1>(acc, lanesN);
+    if (valid && subN == 0) Minv[row] = 1.0 / (d.Pdiag[row] + sigma + acc.a[0]);
+  }
+}
+
+// ------------------------------------------------------------------ the ADMM kernel
+__global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const SolveCfg c) {
+  __shared__ RedSmem sm;
+  Grid g;
+  grid_init(g, d);
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+  const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
+  const int lanesA = d.A.lanes, lanesN = d.At.lanes;
+  const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+
+  double rho = d.state->rho;
+  const double cost_c = d.state->c, cost_cinv = d.state->cinv;
+  long long interval = d.state->adaptive_interval;
+  long long rho_updates = d.state->rho_updates;
+  int refresh = 1;  // first PCG of a launch always rebuilds z_tilde and the residual from scratch
+  const PcgVecs pv{d.r, d.uu, d.p, d.s, d.w, d.t, d.tr, d.Ap};
+  const unsigned long long t_start = globaltimer_ns();
+
+  if (!c.warm_start) {  // cold_start
+    for (int j = n0 + tid; j < n1; j += nth) { d.x[j] = 0.0; d.xt[j] = 0.0; }
+    for (int i = m0 + tid; i < m1; i += nth) { d.z[i] = 0.0; d.y[i] = 0.0; d.zt[i] = 0.0; }
+  }
+  grid_barrier(g);
+
+  InfoScalars S;
+  S.pri_res = S.dua_res = S.obj_val = 0.0;
+  long long status = ST_UNSOLVED, info_iter = 0, cg_total = 0, cg_solves = 0, checks = 0, log_rows = 0, refreshes = 0;
+  double rho_est = rho, elapsed = 0.0;
+  bool can_check = false, can_print = false;
+  long long it;
+  for (it = 1; it <= c.max_iter; it++) {
+    // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde)
+    for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
+    if (refresh && d.m > 0) {
+      for (int base = m0; base < m1; base += ngrpA) {
+        const int row = base + grpA;
+        const bool valid = row < m1;
+        Acc<1> acc;
+        acc.a[0] = 0.0;
+        row_accumulate<1>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc,
+                          [&](Acc<1> &ac, int cc, double a) { ac.a[0] += a * d.xt[cc]; });
+        group_reduce<1>(acc, lanesA);
+        if (valid && subA == 0) {
+          d.zt[row] = acc.a[0];
+          d.tr[row] = d.rho_vec[row] * acc.a[0];
+        }
+      }
+    }
+    grid_barrier(g);
+    // ---- P2: b = sigma x - q + A' wv ; r = b - K x_tilde (refresh) or r += b - b_old
+    double red3[3] = {0.0, 0.0, 0.0};
+    for (int base = n0; base < n1; base += ngrpN) {
+      const int row = base + grpN;
+      const bool valid = row < n1;
+      Acc<2> acc;
+      acc.a[0] = acc.a[1] = 0.0;
+      if (refresh) {
+        row_accumulate<2>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<2> &ac, int cc, double a) { ac.a[1] += a * d.xt[cc]; });
+        if (d.m > 0)
+          row_accumulate<2>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                            [&](Acc<2> &ac, int cc, double a) {
+                              ac.a[0] += a * d.wv[cc];
+                              ac.a[1] += a * d.tr[cc];
+                            });
+      } else if (d.m > 0) {
+        row_accumulate<2>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<2> &ac, int cc, double a) { ac.a[0] += a * d.wv[cc]; });
+      }
+      group_reduce<2>(acc, lanesN);
+      if (valid && subN == 0) {
+        const double bj = c.sigma * d.x[row] - d.q[row] + acc.a[0];
+        double rj;
+        if (refresh) rj = bj - (acc.a[1] + c.sigma * d.xt[row]);
+        else rj = d.r[row] + (bj - d.b[row]);
+        d.b[row] = bj;
+        d.r[row] = rj;
+        const double uj = d.Minv[row] * rj;
+        d.uu[row] = uj;
+        red3[0] += rj * uj;
+        red3[1] = fmax(red3[1], fabs(rj));
+        red3[2] = fmax(red3[2], fabs(bj));
+      }
+    }
+    reduce_and_barrier<3>(g, sm, red3, 0x6u);
+    refreshes += refresh;
+    refresh = 0;
+    {
+      const double thresh = fmax(c.pcg_rel_tol * red3[2], c.pcg_abs_tol);
+      const int ncg = pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1], thresh,
+                              c.pcg_max_iter, m0, m1, n0, n1);
+      cg_total += ncg;
+      cg_solves++;
+    }
+    // ---- Z: x, z, y updates (rows a6-a8); dy is stored already projected on the polar of the
+    //         recession cone of [l,u] (is_primal_infeasible does that projection in place)
+    for (int i = m0 + tid; i < m1; i += nth) {
+      const double zti = d.zt[i], zi = d.z[i], yi = d.y[i], ri = d.rho_vec[i], rinv = d.rho_inv[i];
+      const double li = d.l[i], ui = d.u[i];
+      const double zh = c.alpha * zti + (1.0 - c.alpha) * zi;
+      const double zn = fmin(fmax(zh + rinv * yi, li), ui);
+      double dyi = ri * (zh - zn);
+      d.y[i] = yi + dyi;
+      d.z[i] = zn;
+      if (ui > kInfty * kMinScaling) {
+        if (li < -kInfty * kMinScaling) dyi = 0.0;
+        else dyi = fmin(dyi, 0.0);
+      } else if (li < -kInfty * kMinScaling) {
+        dyi = fmax(dyi, 0.0);
+      }
+      d.dy[i] = dyi;
+    }
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double xj = d.x[j];
+      const double xn = c.alpha * d.xt[j] + (1.0 - c.alpha) * xj;
+      d.dx[j] = xn - xj;
+      d.x[j] = xn;
+    }
+    {
+      double redt[1] = {0.0};
+      if (b == 0 && tid == 0) redt[0] = (double)(globaltimer_ns() - t_start) * 1e-9;
+      reduce_and_barrier<1>(g, sm, redt, 0x1u);
+      elapsed = redt[0];
+    }
+    if (c.time_limit_s > -1e29 && elapsed >= c.time_limit_s) {
+      status = ST_TIME_LIMIT;
+      can_check = false;
+      can_print = false;
+      break;
+    }
+    can_check = c.check_termination && (it % c.check_termination == 0);
+    can_print = c.verbose && ((it % kPrintInterval == 0) || it == 1);
+    if (can_check || can_print) {
+      compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      info_iter = it;
+      checks++;
+      if (can_print && b == 0 && tid == 0 && log_rows < kLogRows) {
+        double *row = d.info->log[log_rows];
+        row[0] = (double)it; row[1] = S.obj_val; row[2] = S.pri_res; row[3] = S.dua_res; row[4] = rho; row[5] = elapsed;
+      }
+      if (can_print && log_rows < kLogRows) log_rows++;
+      if (can_check) {
+        status = check_termination(S, c, d.m, cost_c, cost_cinv, false);
+        if (status != ST_UNSOLVED) break;
+      }
+    }
+    if (c.adaptive_rho && interval == 0 && elapsed > c.adaptive_time_s) {
+      const long long N = c.check_termination ? c.check_termination : 25;
+      const double xx = (double)it + 0.5 * (double)N;
+      interval = (long long)(xx - fmod(xx, (double)N));
+      if (interval < c.check_termination) interval = c.check_termination;
+    }
+    if (c.adaptive_rho && interval && (it % interval == 0)) {
+      if (!can_check && !can_print) {
+        compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+        info_iter = it;
+        checks++;
+      }
+      const double rho_new = rho_estimate(S, rho);
+      rho_est = rho_new;
+      if (rho_new > rho * c.adaptive_rho_tolerance || rho_new < rho / c.adaptive_rho_tolerance) {
+        rho = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+        rho_updates++;
+        for (int i = m0 + tid; i < m1; i += nth) {
+          const int ct = d.ctype[i];
+          if (ct == 0) { d.rho_vec[i] = rho; d.rho_inv[i] = 1.0 / rho; }
+          else if (ct == 1) { d.rho_vec[i] = kRhoEqOverIneq * rho; d.rho_inv[i] = 1.0 / (kRhoEqOverIneq * rho); }
+        }
+        grid_barrier(g);
+        precond_rows(d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        refresh = 1;  // K changed: the residual recurrence is void
+      }
+    }
+    if (c.refresh_every > 0 && (it % c.refresh_every == 0)) refresh = 1;
+  }
+  if (!can_check) {
+    if (!can_print) {
+      compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      info_iter = it - 1;
+      checks++;
+    }
+    const long long s2 = check_termination(S, c, d.m, cost_c, cost_cinv, false);
+    if (s2 != ST_UNSOLVED) status = s2;
+  }
+  rho_est = rho_estimate(S, rho);
+  if (status == ST_UNSOLVED) {
+    const long long s2 = check_termination(S, c, d.m, cost_c, cost_cinv, true);
+    status = (s2 != ST_UNSOLVED) ? s2 : ST_MAX_ITER;
+  } else if (status == ST_TIME_LIMIT) {
+    const long long s2 = check_termination(S, c, d.m, cost_c, cost_cinv, true);
+    if (s2 != ST_UNSOLVED) status = s2;
+  }
+  double obj_val = S.obj_val;
+  if (status == ST_NON_CVX) obj_val = nan("");
+  if (status == ST_PINF || status == ST_PINF_INACC) obj_val = kInfty;
+  if (status == ST_DINF || status == ST_DINF_INACC) obj_val = -kInfty;
+
+  // ---- store_solution (row a16)
+  const bool unscale = c.scaling && !c.scaled_termination;
+  const bool pinf = (status == ST_PINF || status == ST_PINF_INACC), dinf = (status == ST_DINF || status == ST_DINF_INACC);
+  const bool has_sol = !(pinf || dinf || status == ST_NON_CVX);
+  if (has_sol) {
+    for (int j = n0 + tid; j < n1; j += nth) d.sol_x[j] = c.scaling ? d.D[j] * d.x[j] : d.x[j];
+    for (int i = m0 + tid; i < m1; i += nth) d.sol_y[i] = c.scaling ? cost_cinv * d.E[i] * d.y[i] : d.y[i];
+  } else {
+    const double qnan = nan("");
+    for (int j = n0 + tid; j < n1; j += nth) {
+      d.sol_x[j] = qnan;
+      if (dinf) d.dx[j] = (unscale ? d.D[j] : 1.0) * d.dx[j] / S.ndx_t;
+      d.x[j] = 0.0;
+      d.xt[j] = 0.0;
+    }
+    for (int i = m0 + tid; i < m1; i += nth) {
+      d.sol_y[i] = qnan;
+      if (pinf) d.dy[i] = (unscale ? d.E[i] : 1.0) * d.dy[i] / S.ndy_t;
+      d.z[i] = 0.0;
+      d.y[i] = 0.0;
+      d.zt[i] = 0.0;
+    }
+  }
+  if (b == 0 && tid == 0) {
+    DevInfo *I = d.info;
+    I->iter = info_iter;
+    I->status_val = status;
+    I->obj_val = obj_val;
+    I->pri_res = S.pri_res;
+    I->dua_res = S.dua_res;
+    I->rho_estimate = rho_est;
+    I->rho_updates = rho_updates;
+    I->rho = rho;
+    I->adaptive_interval = interval;
+    I->cg_iters = cg_total;
+    I->cg_solves = cg_solves;
+    I->checks = checks;
+    I->refreshes = refreshes;
+    I->elapsed_s = (double)(globaltimer_ns() - t_start) * 1e-9;
+    I->log_rows = log_rows;
+    d.state->rho = rho;
+    d.state->rho_updates = rho_updates;
+    d.state->adaptive_interval = interval;
+    d.state->needs_refresh = 0;
+  }
+}
+
+// ------------------------------------------------------------------ setup-time curvature probe
+// libosqp fails osqp_setup when the LDL' of the KKT matrix has a wrong-sign pivot, i.e. when
+// P + sigma I is not positive definite (test/non_convex.jl:13-21).  Without a factorisation we
+// run CG on (P + sigma I) v = b for a pseudo-random b: CG's pivots p'(P+sigma I)p are the pivots
+// of the Lanczos tridiagonal, so a non-positive one appears as soon as the smallest Ritz value
+// crosses zero (exact after n steps; extreme eigenvalues converge first).
+__global__ void __launch_bounds__(1024, 1) pd_probe_kernel(const DevPtrs d, double sigma, int max_it) {
+  __shared__ RedSmem sm;
+  Grid g;
+  grid_init(g, d);
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+  const int n0 = d.n_start[b], n1 = d.n_start[b + 1];
+  const int lanesN = d.At.lanes;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  double red[1] = {0.0};
+  for (int j = n0 + tid; j < n1; j += nth) {
+    unsigned h = (unsigned)j * 2654435761u + 12345u;
+    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
+    const double v = ((double)(h & 0xFFFFFF) / 16777216.0) - 0.5 + 1e-3;
+    d.r[j] = v;
+    d.p[j] = v;
+    red[0] += v * v;
+  }
+  reduce_and_barrier<1>(g, sm, red, 0u);
+  double rr = red[0];
+  const double rr0 = rr;
+  int failed = 0;
+  for (int it = 0; it < max_it && rr > 1e-26 * rr0; it++) {
+    red[0] = 0.0;
+    for (int base = n0; base < n1; base += ngrpN) {
+      const int row = base + grpN;
+      const bool valid = row < n1;
+      Acc<1> acc;
+      acc.a[0] = 0.0;
+      row_accumulate<1>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * d.p[c]; });
+      group_reduce<1>(acc, lanesN);
+      if (valid && subN == 0) {
+        const double pj = d.p[row];
+        const double wj = acc.a[0] + sigma * pj;
+        d.w[row] = wj;
+        red[0] += wj * pj;
+      }
+    }
+    reduce_and_barrier<1>(g, sm, red, 0u);
+    const double pw = red[0];
+    if (!(pw > 0.0)) {
+      failed = 1;
+      break;
+    }
+    const double a = rr / pw;
+    red[0] = 0.0;
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double rj = d.r[j] - a * d.w[j];
+      d.r[j] = rj;
+      red[0] += rj * rj;
+    }
+    reduce_and_barrier<1>(g, sm, red, 0u);
+    const double beta = red[0] / rr;
+    rr = red[0];
+    for (int j = n0 + tid; j < n1; j += nth) d.p[j] = d.r[j] + beta * d.p[j];
+    grid_barrier(g);
+  }
+  if (b == 0 && tid == 0) d.state->pd_check_failed = failed;
+}
+
+// ------------------------------------------------------------------ polish (row a12)
+// Active-set guess as in libosqp (z - l < -y lower-active, u - z < y upper-active), then the
+// equality-constrained QP  min 1/2 x'Px + q'x  s.t. A_act x = b_act  is solved by a proximal
+// method of multipliers whose inner systems  (P + delta I + penalty A_act'A_act) x = rhs  reuse
+// the PCG above (rho := penalty on active rows, 0 elsewhere).  libosqp factorises the
+// delta-regularised KKT and applies `polish_refine_iter` refinement steps; both converge to
+// the same KKT point of the active-set QP.
+__global__ void __launch_bounds__(1024, 1) polish_kernel(const DevPtrs d, const PolishCfg c, const SolveCfg sc,
+                                                         PolishOut *out) {
+  __shared__ RedSmem sm;
+  Grid g;
+  grid_init(g, d);
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+  const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
+  const int lanesA = d.A.lanes, lanesN = d.At.lanes;
+  const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  const double cost_c = d.state->c, cost_cinv = d.state->cinv;
+  const PcgVecs pv{d.r, d.uu, d.p, d.s, d.w, d.t, d.tr, d.Ap};
+
+  // ---- active sets, start point (ADMM x, multipliers y on active rows)
+  double cnt[1] = {0.0};
+  for (int i = m0 + tid; i < m1; i += nth) {
+    const double zi = d.z[i], yi = d.y[i], li = d.l[i], ui = d.u[i];
+    const bool low = (zi - li < -yi), upp = (ui - zi < yi);
+    // libosqp gives lower-active precedence when both tests fire
+    const bool act = low || upp;
+    d.pol_rho[i] = act ? c.penalty : 0.0;
+    d.pol_b[i] = low ? li : (upp ? ui : 0.0);
+    d.pol_y[i] = act ? yi : 0.0;
+    cnt[0] += act ? 1.0 : 0.0;
+  }
+  for (int j = n0 + tid; j < n1; j += nth) d.pol_x[j] = d.x[j];
+  reduce_and_barrier<1>(g, sm, cnt, 0u);
+  const long long n_active = (long long)(cnt[0] + 0.5);
+  // preconditioner for K_pol
+  precond_rows(d, d.pol_rho, c.delta, d.pol_rhs /* reused as Minv_pol below */, n0, n1);
+  double *Minv_pol = d.pol_rhs;
+  long long cg_total = 0;
+  for (int outer = 0; outer <= c.refine_iter; outer++) {
+    // z = A x (fresh), wv = penalty*(b - z) - y on active rows : K dx = -(P x + q + delta*0) + A'(wv) ...
+    // Solve for the full new x with warm start x:  r = rhs - K x where
+    //   rhs = -q + delta x_k + A'(penalty b - y),  K = P + delta I + A' penalty A
+    //   => r = -q - P x + A'(penalty (b - A x) - y)
+    if (d.m > 0) {
+      for (int base = m0; base < m1; base += ngrpA) {
+        const int row = base + grpA;
+        const bool valid = row < m1;
+        Acc<1> acc;
+        acc.a[0] = 0.0;
+        row_accumulate<1>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc,
+                          [&](Acc<1> &ac, int cc, double a) { ac.a[0] += a * d.pol_x[cc]; });
+        group_reduce<1>(acc, lanesA);
+        if (valid && subA == 0) {
+          d.pol_z[row] = acc.a[0];
+          d.wv[row] = d.pol_rho[row] * (d.pol_b[row] - acc.a[0]) - d.pol_y[row];
+        }
+      }
+    }
+    grid_barrier(g);
+    double red3[3] = {0.0, 0.0, 0.0};
+    for (int base = n0; base < n1; base += ngrpN) {
+      const int row = base + grpN;
+      const bool valid = row < n1;
+      Acc<2> acc;
+      acc.a[0] = acc.a[1] = 0.0;
+      row_accumulate<2>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                        [&](Acc<2> &ac, int cc, double a) { ac.a[1] += a * d.pol_x[cc]; });
+      if (d.m > 0)
+        row_accumulate<2>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<2> &ac, int cc, double a) { ac.a[0] += a * d.wv[cc]; });
+      group_reduce<2>(acc, lanesN);
+      if (valid && subN == 0) {
+        const double rj = -d.q[row] - acc.a[1] + acc.a[0];
+        d.r[row] = rj;
+        const double uj = Minv_pol[row] * rj;
+        d.uu[row] = uj;
+        red3[0] += rj * uj;
+        red3[1] = fmax(red3[1], fabs(rj));
+        red3[2] = fmax(red3[2], fabs(d.q[row]) + fabs(acc.a[1]));  // scale of the stationarity terms, penalty-free
+      }
+    }
+    reduce_and_barrier<3>(g, sm, red3, 0x6u);
+    const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
+    cg_total += pcg_run(g, sm, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1], thresh,
+                        c.pcg_max_iter, m0, m1, n0, n1);
+    // multiplier step on active rows: y += penalty (A x - b)
+    for (int i = m0 + tid; i < m1; i += nth)
+      if (d.pol_rho[i] > 0.0) d.pol_y[i] += d.pol_rho[i] * (d.pol_z[i] - d.pol_b[i]);
+    grid_barrier(g);
+  }
+  // ---- z = A x exactly, then project (z, y) on the normal cone of [l, u]
+  if (d.m > 0) {
+    for (int base = m0; base < m1; base += ngrpA) {
+      const int row = base + grpA;
+      const bool valid = row < m1;
+      Acc<1> acc;
+      acc.a[0] = 0.0;
+      row_accumulate<1>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc,
+                        [&](Acc<1> &ac, int cc, double a) { ac.a[0] += a * d.pol_x[cc]; });
+      group_reduce<1>(acc, lanesA);
+      if (valid && subA == 0) {
+        const double tt = acc.a[0] + d.pol_y[row];
+        const double zn = fmin(fmax(tt, d.l[row]), d.u[row]);
+        d.pol_z[row] = zn;
+        d.pol_y[row] = tt - zn;
+      }
+    }
+  }
+  // compute_info reads dx / dy for the infeasibility products; they are irrelevant here
+  grid_barrier(g);
+  InfoScalars S;
+  compute_info(g, sm, d, sc, cost_c, cost_cinv, d.pol_x, d.pol_z, d.pol_y, m0, m1, n0, n1, S);
+  // residuals of the ADMM iterate were published by admm_kernel
+  const double pri0 = d.info->pri_res, dua0 = d.info->dua_res;
+  const bool ok = (S.pri_res < pri0 && S.dua_res < dua0) || (S.pri_res < pri0 && dua0 < 1e-10) ||
+                  (S.dua_res < dua0 && pri0 < 1e-10);
+  if (ok) {
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double xj = d.pol_x[j];
+      d.x[j] = xj;
+      d.xt[j] = xj;
+      d.sol_x[j] = sc.scaling ? d.D[j] * xj : xj;
+    }
+    for (int i = m0 + tid; i < m1; i += nth) {
+      d.z[i] = d.pol_z[i];
+      d.zt[i] = d.pol_z[i];
+      d.y[i] = d.pol_y[i];
+      d.sol_y[i] = sc.scaling ? cost_cinv * d.E[i] * d.pol_y[i] : d.pol_y[i];
+    }
+  }
+  grid_barrier(g);
+  if (b == 0 && tid == 0) {
+    out->n_active = n_active;
+    out->obj_val = S.obj_val;
+    out->pri_res = S.pri_res;
+    out->dua_res = S.dua_res;
+    out->cg_iters = cg_total;
+    out->success = ok ? 1 : 0;
+    d.state->needs_refresh = 1;
+  }
+}
+
+// ------------------------------------------------------------------ standalone SpMV (profiling / parity)
+// which: 0  out = A in (m) | 1  out = A' in (n) | 2  out = (P + sigma I) in (n)
+__global__ void __launch_bounds__(1024, 1) spmv_kernel(const DevPtrs d, int which, const double *in, double *out,
+                                                       double sigma) {
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+  const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
+  const int lanesA = d.A.lanes, lanesN = d.At.lanes;
+  const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
+  const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
+  if (which == 0) {
+    for (int base = m0; base < m1; base += ngrpA) {
+      const int row = base + grpA;
+      const bool valid = row < m1;
+      Acc<1> acc;
+      acc.a[0] = 0.0;
+      row_accumulate<1>(d.A.rowptr, d.A.col, d.A.val, row, valid, subA, lanesA, acc,
+                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * in[c]; });
+      group_reduce<1>(acc, lanesA);
+      if (valid && subA == 0) out[row] = acc.a[0];
+    }
+  } else {
+    for (int base = n0; base < n1; base += ngrpN) {
+      const int row = base + grpN;
+      const bool valid = row < n1;
+      Acc<1> acc;
+      acc.a[0] = 0.0;
+      if (which == 1)
+        row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * in[c]; });
+      else
+        row_accumulate<1>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * in[c]; });
+      group_reduce<1>(acc, lanesN);
+      if (valid && subN == 0) out[row] = acc.a[0] + (which == 2 ? sigma * in[row] : 0.0);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ setup kernels (row a2, a3): simple grid-stride
+__device__ __forceinline__ double limit_scaling(double a) {
+  a = a < kMinScaling ? 1.0 : a;
+  return a > kMaxScaling ? kMaxScaling : a;
+}
+
+__global__ void k_copy_vals(const DevPtrs d) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long k = tid; k < d.A.nnz; k += nth) { d.A.val[k] = d.A.val0[k]; d.At.val[k] = d.At.val0[k]; }
+  for (long long k = tid; k < d.P.nnz; k += nth) d.P.val[k] = d.P.val0[k];
+  for (long long j = tid; j < d.n; j += nth) { d.q[j] = d.q0[j]; d.D[j] = 1.0; d.Dinv[j] = 1.0; }
+  for (long long i = tid; i < d.m; i += nth) { d.E[i] = 1.0; d.Einv[i] = 1.0; }
+  if (tid == 0) { d.state->c = 1.0; d.state->cinv = 1.0; }
+}
+
+// one warp per row: infinity norms of the KKT columns -> dtmp, etmp = 1/sqrt(limit(norm))
+__global__ void k_ruiz_norms(const DevPtrs d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < (long long)d.n + d.m; r += nwarps) {
+    double mx = 0.0;
+    if (r < d.n) {
+      for (int k = d.P.rowptr[r] + lane; k < d.P.rowptr[r + 1]; k += 32) mx = fmax(mx, fabs(d.P.val[k]));
+      if (d.m > 0)
+        for (int k = d.At.rowptr[r] + lane; k < d.At.rowptr[r + 1]; k += 32) mx = fmax(mx, fabs(d.At.val[k]));
+    } else {
+      const long long i = r - d.n;
+      for (int k = d.A.rowptr[i] + lane; k < d.A.rowptr[i + 1]; k += 32) mx = fmax(mx, fabs(d.A.val[k]));
+    }
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+      const double s = 1.0 / sqrt(limit_scaling(mx));
+      if (r < d.n) d.dtmp[r] = s;
+      else d.etmp[r - d.n] = s;
+    }
+  }
+}
+
+// P <- Dt P Dt, A <- Et A Dt (same rounding order as premult then postmult), q, D, E
+__global__ void k_ruiz_apply(const DevPtrs d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < (long long)d.n + d.m; r += nwarps) {
+    if (r < d.n) {
+      const double dr = d.dtmp[r];
+      for (int k = d.P.rowptr[r] + lane; k < d.P.rowptr[r + 1]; k += 32) {
+        // symmetric full storage: entry (r, c) must get the same bits as (c, r): scale by the
+        // smaller index first, then the larger (the upper-triangle order row <= col of the oracle)
+        const int cidx = d.P.col[k];
+        const double dc = d.dtmp[cidx];
+        const double first = (r <= cidx) ? dr : dc, second = (r <= cidx) ? dc : dr;
+        d.P.val[k] = (d.P.val[k] * first) * second;
+      }
+      if (d.m > 0)
+        for (int k = d.At.rowptr[r] + lane; k < d.At.rowptr[r + 1]; k += 32)
+          d.At.val[k] = (d.At.val[k] * d.etmp[d.At.col[k]]) * dr;
+      if (lane == 0) { d.q[r] *= dr; d.D[r] *= dr; }
+    } else {
+      const long long i = r - d.n;
+      const double er = d.etmp[i];
+      for (int k = d.A.rowptr[i] + lane; k < d.A.rowptr[i + 1]; k += 32)
+        d.A.val[k] = (d.A.val[k] * er) * d.dtmp[d.A.col[k]];
+      if (lane == 0) d.E[i] *= er;
+    }
+  }
+}
+
+// cost normalisation: c_temp = 1 / limit(max(mean_j |P_:j|inf, limit(|q|inf)))   (single block)
+__global__ void __launch_bounds__(1024) k_ruiz_cost(const DevPtrs d) {
+  __shared__ double ssum[32], smax[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  double sum = 0.0, qmax = 0.0;
+  for (int r = warp; r < d.n; r += nwarps) {
+    double mx = 0.0;
+    for (int k = d.P.rowptr[r] + lane; k < d.P.rowptr[r + 1]; k += 32) mx = fmax(mx, fabs(d.P.val[k]));
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) { sum += mx; qmax = fmax(qmax, fabs(d.q[r])); }
+  }
+  if (lane == 0) { ssum[warp] = sum; smax[warp] = qmax; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int w = 0; w < nwarps; w++) { s += ssum[w]; q = fmax(q, smax[w]); }
+    double ct = s / (double)d.n;
+    ct = limit_scaling(fmax(ct, limit_scaling(q)));
+    ct = 1.0 / ct;
+    d.dtmp[0] = ct;  // dtmp is free between Ruiz passes
+    d.state->c *= ct;
+  }
+}
+
+__global__ void k_ruiz_cost_apply(const DevPtrs d) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const double ct = d.dtmp[0];
+  for (long long k = tid; k < d.P.nnz; k += nth) d.P.val[k] *= ct;
+  for (long long j = tid; j < d.n; j += nth) d.q[j] *= ct;
+}
+
+// Dinv, Einv, cinv, P diagonal, scaled bounds
+__global__ void k_scale_finish(const DevPtrs d, int scaling) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long j = tid; j < d.n; j += nth) {
+    if (scaling) d.Dinv[j] = 1.0 / d.D[j];
+    double dg = 0.0;
+    for (int k = d.P.rowptr[j]; k < d.P.rowptr[j + 1]; k++)
+      if (d.P.col[k] == j) dg += d.P.val[k];
+    d.Pdiag[j] = dg;
+  }
+  for (long long i = tid; i < d.m; i += nth) {
+    if (scaling) d.Einv[i] = 1.0 / d.E[i];
+    d.l[i] = scaling ? d.E[i] * d.l0[i] : d.l0[i];
+    d.u[i] = scaling ? d.E[i] * d.u0[i] : d.u0[i];
+  }
+  if (tid == 0) d.state->cinv = 1.0 / d.state->c;
+}
+
+// q <- c D q0 ; l,u <- E l0, E u0
+__global__ void k_scale_vectors(const DevPtrs d, int do_q, int do_bounds, int scaling) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const double c = d.state->c;
+  if (do_q)
+    for (long long j = tid; j < d.n; j += nth) d.q[j] = scaling ? (d.q0[j] * d.D[j]) * c : d.q0[j];
+  if (do_bounds)
+    for (long long i = tid; i < d.m; i += nth) {
+      d.l[i] = scaling ? d.E[i] * d.l0[i] : d.l0[i];
+      d.u[i] = scaling ? d.E[i] * d.u0[i] : d.u0[i];
+    }
+}
+
+// set_rho_vec / update_rho_vec (row a3)
+__global__ void k_set_rho_vec(const DevPtrs d, double rho) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < d.m; i += nth) {
+    const double li = d.l[i], ui = d.u[i];
+    int t;
+    double r;
+    if (li < -kInfty * kMinScaling && ui > kInfty * kMinScaling) { t = -1; r = kRhoMin; }
+    else if (ui - li < kRhoTol) { t = 1; r = kRhoEqOverIneq * rho; }
+    else { t = 0; r = rho; }
+    d.ctype[i] = t;
+    d.rho_vec[i] = r;
+    d.rho_inv[i] = 1.0 / r;
+  }
+}
+__global__ void k_apply_rho(const DevPtrs d, double rho) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < d.m; i += nth) {
+    const int t = d.ctype[i];
+    if (t == 0) { d.rho_vec[i] = rho; d.rho_inv[i] = 1.0 / rho; }
+    else if (t == 1) { d.rho_vec[i] = kRhoEqOverIneq * rho; d.rho_inv[i] = 1.0 / (kRhoEqOverIneq * rho); }
+  }
+}
+
+__global__ void k_precond(const DevPtrs d, double sigma) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long j = warp; j < d.n; j += nwarps) {
+    double s = 0.0;
+    if (d.m > 0)
+      for (int k = d.At.rowptr[j] + lane; k < d.At.rowptr[j + 1]; k += 32) {
+        const double a = d.At.val[k];
+        s += d.rho_vec[d.At.col[k]] * a * a;
+      }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) d.Minv[j] = 1.0 / (d.Pdiag[j] + sigma + s);
+  }
+}
+
+// osqp_warm_start (row a14): x <- Dinv x, y <- c Einv y, z <- A x ; PCG guess x_tilde := x
+__global__ void k_warm_start_xy(const DevPtrs d, const double *x_in, const double *y_in, int scaling) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const double c = d.state->c;
+  if (x_in)
+    for (long long j = tid; j < d.n; j += nth) {
+      const double v = scaling ? x_in[j] * d.Dinv[j] : x_in[j];
+      d.x[j] = v;
+      d.xt[j] = v;
+    }
+  if (y_in)
+    for (long long i = tid; i < d.m; i += nth) d.y[i] = scaling ? (y_in[i] * d.Einv[i]) * c : y_in[i];
+  if (tid == 0) d.state->needs_refresh = 1;
+}
+__global__ void k_warm_start_z(const DevPtrs d) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = warp; i < d.m; i += nwarps) {
+    double s = 0.0;
+    for (int k = d.A.rowptr[i] + lane; k < d.A.rowptr[i + 1]; k += 32) s += d.A.val[k] * d.x[d.A.col[k]];
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { d.z[i] = s; d.zt[i] = s; }
+  }
+}
+__global__ void k_cold_start(const DevPtrs d) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long j = tid; j < d.n; j += nth) { d.x[j] = 0.0; d.xt[j] = 0.0; d.dx[j] = 0.0; }
+  for (long long i = tid; i < d.m; i += nth) { d.z[i] = 0.0; d.y[i] = 0.0; d.zt[i] = 0.0; d.dy[i] = 0.0; }
+}
+
+// dst[map ? map[idx[k]] : idx[k]] = vals[k]   (idx == nullptr: identity)
+__global__ void k_scatter(double *dst, const double *vals, const long long *idx, const int *map, long long k) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long e = tid; e < k; e += nth) {
+    const long long src = idx ? idx[e] : e;
+    const long long pos = map ? (long long)map[src] : src;
+    if (pos >= 0) dst[pos] = vals[e];
+  }
+}
+
+inline int ew_grid(long long work) {
+  long long g = (work + 255) / 256;
+  if (g < 1) g = 1;
+  if (g > 148 * 8) g = 148 * 8;
+  return (int)g;
+}
+
+template <typename... Args>
+cudaError_t coop_launch(void (*kernel)(Args...), LaunchGeom g, cudaStream_t st, Args... args) {
+  void *params[] = {(void *)&args...};
+  return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, 0, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ host wrappers
+cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma, cudaStream_t st) {
+  const long long rows = (long long)d.n + d.m;
+  const int gw = ew_grid(rows * 32), ge = ew_grid(d.A.nnz + d.P.nnz + rows);
+  k_copy_vals<<<ge, 256, 0, st>>>(d);
+  for (int it = 0; it < scaling_iters; it++) {
+    k_ruiz_norms<<<gw, 256, 0, st>>>(d);
+    k_ruiz_apply<<<gw, 256, 0, st>>>(d);
+    k_ruiz_cost<<<1, 1024, 0, st>>>(d);
+    k_ruiz_cost_apply<<<ge, 256, 0, st>>>(d);
+  }
+  k_scale_finish<<<ew_grid(rows), 256, 0, st>>>(d, scaling_iters > 0 ? 1 : 0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scale_vectors(const DevPtrs &d, int do_q, int do_bounds, cudaStream_t st) {
+  // `scaling` on/off is encoded in D/E/c being 1, so the scaled formulas are always right
+  k_scale_vectors<<<ew_grid((long long)d.n + d.m), 256, 0, st>>>(d, do_q, do_bounds, 1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_set_rho_vec(const DevPtrs &d, double rho, int, cudaStream_t st) {
+  if (d.m > 0) k_set_rho_vec<<<ew_grid(d.m), 256, 0, st>>>(d, rho);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_apply_rho(const DevPtrs &d, double rho, cudaStream_t st) {
+  if (d.m > 0) k_apply_rho<<<ew_grid(d.m), 256, 0, st>>>(d, rho);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st) {
+  k_precond<<<ew_grid((long long)d.n * 32), 256, 0, st>>>(d, sigma);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st) {
+  return coop_launch(pd_probe_kernel, g, st, d, sigma, max_it);
+}
+
+cudaError_t launch_warm_start(const DevPtrs &d, const double *x_in, const double *y_in, int scaling, cudaStream_t st) {
+  k_warm_start_xy<<<ew_grid((long long)d.n + d.m), 256, 0, st>>>(d, x_in, y_in, scaling);
+  if (x_in && d.m > 0) k_warm_start_z<<<ew_grid((long long)d.m * 32), 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_cold_start(const DevPtrs &d, cudaStream_t st) {
+  k_cold_start<<<ew_grid((long long)d.n + d.m), 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_scatter_values(double *dst, const double *vals, const long long *idx, const int *map, long long k,
+                                  cudaStream_t st) {
+  if (k > 0) k_scatter<<<ew_grid(k), 256, 0, st>>>(dst, vals, idx, map, k);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
+  return coop_launch(admm_kernel, g, st, d, cfg);
+}
+
+cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
+                        cudaStream_t st) {
+  spmv_kernel<<<g.grid, g.block, 0, st>>>(d, which, in, out, sigma);
+  return cudaGetLastError();
+}
+
+int max_coop_blocks_per_sm(int block) {
+  int nb = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, admm_kernel, block, 0) != cudaSuccess) return 0;
+  int nb2 = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, polish_kernel, block, 0) != cudaSuccess) return 0;
+  return nb < nb2 ? nb : nb2;
+}
+
+cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
+                          cudaStream_t st) {
+  return coop_launch(polish_kernel, g, st, d, cfg, sc, out);
+}
+
+}  // namespace osqpb200

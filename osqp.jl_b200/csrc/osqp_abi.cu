@@ -1,0 +1,973 @@
+// osqp_abi.cu -- the C ABI of include/osqp.h on top of the CUDA engine (kernels.cu).
+//
+// Host-side responsibilities only: validate, marshal the caller's Int64 CSC into the int32 CSR
+// layouts the kernels stream, keep the five host-visible Workspace fields Julia dereferences
+// (src/interface.jl:176-205) in pinned memory, turn CUDA errors into non-zero exit codes.  No
+// arithmetic of the solver runs on the host; without a usable GPU every entry point fails loudly.
+#include "engine.cuh"
+#include "osqp.h"
+#include "osqp_b200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace osqpb200;
+
+namespace {
+
+constexpr double kRhoMin = 1e-6, kRhoMax = 1e6;
+
+double now_s() {
+  using namespace std::chrono;
+  return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+#define CU_OK(expr)                                                                              \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      fprintf(stderr, "ERROR in %s: CUDA failure '%s' at %s:%d (%s)\n", __func__,                \
+              cudaGetErrorString(_e), __FILE__, __LINE__, #expr);                                \
+      return 100 + (c_int)_e;                                                                    \
+    }                                                                                            \
+  } while (0)
+
+struct Engine {
+  OSQPWorkspace pub;  // MUST be first: the ABI pointer is &pub
+  OSQPData data_pub;
+  OSQPSettings st;
+  OSQPInfo info;
+  OSQPSolution sol_pub;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr;
+  DevPtrs d;
+  LaunchGeom geom;
+  std::vector<void *> dev_allocs, host_allocs;
+  // pinned host mirrors
+  double *h_sol_x = nullptr, *h_sol_y = nullptr, *h_dx = nullptr, *h_dy = nullptr;
+  DevInfo *h_info = nullptr;
+  PolishOut *h_pol = nullptr;
+  DevState *h_state = nullptr;
+  PolishOut *d_pol = nullptr;
+  // host copies of the bounds as passed (l <= u validation on updates)
+  std::vector<double> l0, u0;
+  // csc position -> device position maps
+  int *mapA = nullptr, *mapP1 = nullptr, *mapP2 = nullptr;
+  long long nnzA = 0, nnzPtriu = 0;
+  // staging for value / index uploads
+  double *stage_val = nullptr;
+  long long *stage_idx = nullptr;
+  long long stage_cap = 0;
+  // engine controls
+  double pcg_rel_tol = 0.0 /* 0 = auto: min(1e-7, 0.01*max(eps_abs, eps_rel)) */, pcg_abs_tol = 1e-14;
+  int pcg_max_iter = 0, refresh_every = 25;
+  double polish_penalty = 1e4;
+  bool first_run = true, clear_update_time = false;
+  OSQPB200Profile prof;
+};
+
+Engine *E(OSQPWorkspace *w) { return reinterpret_cast<Engine *>(w); }
+const Engine *E(const OSQPWorkspace *w) { return reinterpret_cast<const Engine *>(w); }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+template <typename T>
+cudaError_t dalloc(Engine &e, T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  void *q = nullptr;
+  cudaError_t err = cudaMalloc(&q, count * sizeof(T));
+  if (err != cudaSuccess) return err;
+  e.dev_allocs.push_back(q);
+  *p = reinterpret_cast<T *>(q);
+  return cudaMemsetAsync(q, 0, count * sizeof(T), e.stream);
+}
+template <typename T>
+cudaError_t halloc(Engine &e, T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  void *q = nullptr;
+  cudaError_t err = cudaMallocHost(&q, count * sizeof(T));
+  if (err != cudaSuccess) return err;
+  e.host_allocs.push_back(q);
+  memset(q, 0, count * sizeof(T));
+  *p = reinterpret_cast<T *>(q);
+  return cudaSuccess;
+}
+
+void destroy(Engine *e) {
+  if (!e) return;
+  DeviceGuard guard(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (void *p : e->dev_allocs) cudaFree(p);
+  for (void *p : e->host_allocs) cudaFreeHost(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->ev2) cudaEventDestroy(e->ev2);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+void update_status(OSQPInfo &info, c_int v) {
+  info.status_val = v;
+  const char *s = "unsolved";
+  switch (v) {
+    case OSQP_SOLVED: s = "solved"; break;
+    case OSQP_SOLVED_INACCURATE: s = "solved inaccurate"; break;
+    case OSQP_PRIMAL_INFEASIBLE: s = "primal infeasible"; break;
+    case OSQP_PRIMAL_INFEASIBLE_INACCURATE: s = "primal infeasible inaccurate"; break;
+    case OSQP_DUAL_INFEASIBLE: s = "dual infeasible"; break;
+    case OSQP_DUAL_INFEASIBLE_INACCURATE: s = "dual infeasible inaccurate"; break;
+    case OSQP_MAX_ITER_REACHED: s = "maximum iterations reached"; break;
+    case OSQP_TIME_LIMIT_REACHED: s = "run time limit reached"; break;
+    case OSQP_SIGINT: s = "interrupted"; break;
+    case OSQP_NON_CVX: s = "problem non convex"; break;
+    default: break;
+  }
+  memset(info.status, 0, sizeof(info.status));
+  strncpy(info.status, s, sizeof(info.status) - 1);
+}
+
+void reset_info(Engine &e) {
+  e.info.solve_time = 0;
+  e.info.polish_time = 0;
+  update_status(e.info, OSQP_UNSOLVED);
+  e.info.rho_updates = 0;
+  e.h_state->rho_updates = 0;
+}
+
+void begin_update(Engine &e) {
+  if (e.clear_update_time) {
+    e.clear_update_time = false;
+    e.info.update_time = 0.0;
+  }
+}
+
+int validate_data(const OSQPData *d) {
+  if (!d) { fprintf(stderr, "ERROR in osqp_setup: missing data\n"); return 1; }
+  if (!d->P || !d->A || (!d->q && d->n > 0)) { fprintf(stderr, "ERROR in osqp_setup: missing matrix/vector\n"); return 1; }
+  if (d->n <= 0 || d->m < 0) { fprintf(stderr, "ERROR in osqp_setup: n must be positive and m nonnegative\n"); return 1; }
+  if (d->P->m != d->n || d->P->n != d->n) { fprintf(stderr, "ERROR in osqp_setup: P does not have dimension n x n\n"); return 1; }
+  for (c_int j = 0; j < d->n; j++)
+    for (c_int k = d->P->p[j]; k < d->P->p[j + 1]; k++)
+      if (d->P->i[k] > j) { fprintf(stderr, "ERROR in osqp_setup: P is not upper triangular\n"); return 1; }
+  if (d->A->m != d->m || d->A->n != d->n) { fprintf(stderr, "ERROR in osqp_setup: A does not have dimension m x n\n"); return 1; }
+  for (c_int i = 0; i < d->m; i++)
+    if (d->l[i] > d->u[i]) {
+      fprintf(stderr, "ERROR in osqp_setup: lower bound at index %lld is greater than upper bound\n", (long long)i);
+      return 1;
+    }
+  const long long lim = 2147483647LL - 64;
+  if (d->n > lim || d->m > lim || d->A->p[d->n] > lim || 2 * d->P->p[d->n] > lim) {
+    fprintf(stderr, "ERROR in osqp_setup: problem exceeds the engine's int32 index range\n");
+    return 1;
+  }
+  return 0;
+}
+int validate_settings(const OSQPSettings *s) {
+  if (!s) return 1;
+  bool bad = s->scaling < 0 || (s->adaptive_rho != 0 && s->adaptive_rho != 1) || s->adaptive_rho_interval < 0 ||
+             s->adaptive_rho_fraction <= 0 || s->adaptive_rho_tolerance < 1.0 || s->polish_refine_iter < 0 ||
+             s->rho <= 0 || s->sigma <= 0 || s->delta <= 0 || s->max_iter <= 0 || s->eps_abs < 0 ||
+             s->eps_rel < 0 || (s->eps_rel == 0 && s->eps_abs == 0) || s->eps_prim_inf <= 0 ||
+             s->eps_dual_inf <= 0 || s->alpha <= 0 || s->alpha >= 2 ||
+             (s->linsys_solver != QDLDL_SOLVER && s->linsys_solver != MKL_PARDISO_SOLVER) ||
+             (s->verbose != 0 && s->verbose != 1) || (s->scaled_termination != 0 && s->scaled_termination != 1) ||
+             s->check_termination < 0 || (s->warm_start != 0 && s->warm_start != 1) || s->time_limit < 0;
+  if (bad) fprintf(stderr, "ERROR in osqp_setup: invalid settings\n");
+  return bad ? 1 : 0;
+}
+
+double env_double(const char *name, double dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atof(s) : dflt;
+}
+int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+int pow2_lanes(double avg_nnz_per_row) {
+  int forced = env_int("OSQP_B200_LANES", 0);
+  if (forced > 0) return forced;
+  int l = 1;
+  while (l < 32 && (double)l * 4.0 < avg_nnz_per_row) l <<= 1;
+  return l;
+}
+
+// contiguous, weight-balanced split of `rows` rows into `parts` ranges
+void balanced_split(const std::vector<long long> &w_prefix, int rows, int parts, std::vector<int> &start) {
+  start.assign(parts + 1, 0);
+  const long long total = w_prefix[rows];
+  int r = 0;
+  for (int b = 1; b < parts; b++) {
+    const long long target = (long long)((double)total * (double)b / (double)parts);
+    while (r < rows && w_prefix[r] < target) r++;
+    start[b] = r;
+  }
+  start[parts] = rows;
+}
+
+c_int upload_partition(Engine &e, const std::vector<int> &A_rowptr, const std::vector<int> &At_rowptr,
+                       const std::vector<int> &P_rowptr) {
+  const int n = e.d.n, m = e.d.m, grid = e.geom.grid;
+  std::vector<long long> wm(m + 1, 0), wn(n + 1, 0);
+  for (int i = 0; i < m; i++) wm[i + 1] = wm[i] + (A_rowptr[i + 1] - A_rowptr[i]) + 4;
+  for (int j = 0; j < n; j++)
+    wn[j + 1] = wn[j] + (P_rowptr[j + 1] - P_rowptr[j]) + (m > 0 ? At_rowptr[j + 1] - At_rowptr[j] : 0) + 4;
+  std::vector<int> ms, ns;
+  balanced_split(wm, m, grid, ms);
+  balanced_split(wn, n, grid, ns);
+  CU_OK(cudaMemcpyAsync(e.d.m_start, ms.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  CU_OK(cudaMemcpyAsync(e.d.n_start, ns.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  CU_OK(cudaStreamSynchronize(e.stream));  // ms/ns go out of scope
+  return 0;
+}
+
+c_int push_state(Engine &e) {
+  CU_OK(cudaMemcpyAsync(e.d.state, e.h_state, sizeof(DevState), cudaMemcpyHostToDevice, e.stream));
+  return 0;
+}
+c_int pull_state(Engine &e) {
+  CU_OK(cudaMemcpyAsync(e.h_state, e.d.state, sizeof(DevState), cudaMemcpyDeviceToHost, e.stream));
+  CU_OK(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
+// scale_data (a2) + set_rho_vec (a3) + preconditioner; `keep_rho_types`: libosqp's update_P/A keeps rho_vec
+c_int rescale_and_refresh(Engine &e, bool reset_rho_types) {
+  CU_OK(launch_scale_data(e.d, (int)e.st.scaling, e.st.sigma, e.stream));
+  e.prof.launches += 2 + 4 * (int)e.st.scaling;
+  if (reset_rho_types) {
+    CU_OK(launch_set_rho_vec(e.d, e.st.rho, 0, e.stream));
+    e.prof.launches += 1;
+  }
+  CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
+  e.prof.launches += 1;
+  return 0;
+}
+
+void publish(Engine &e) {
+  OSQPWorkspace &p = e.pub;
+  memset(&p, 0, sizeof(p));
+  e.data_pub.n = e.d.n;
+  e.data_pub.m = e.d.m;
+  e.data_pub.P = nullptr;
+  e.data_pub.A = nullptr;
+  e.data_pub.q = nullptr;
+  e.data_pub.l = nullptr;
+  e.data_pub.u = nullptr;
+  e.sol_pub.x = e.h_sol_x;
+  e.sol_pub.y = e.h_sol_y;
+  p.data = &e.data_pub;
+  p.delta_y = e.h_dy;
+  p.delta_x = e.h_dx;
+  p.settings = &e.st;
+  p.solution = &e.sol_pub;
+  p.info = &e.info;
+  p.first_run = e.first_run ? 1 : 0;
+  p.summary_printed = 0;
+}
+
+void print_setup_header(const Engine &e) {
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, e.device);
+  printf("-----------------------------------------------------------------\n");
+  printf("     OSQP ADMM engine for NVIDIA B200 (sm_100a) -- libosqp ABI\n");
+  printf("-----------------------------------------------------------------\n");
+  printf("problem:  variables n = %d, constraints m = %d\n", e.d.n, e.d.m);
+  printf("          nnz(P) + nnz(A) = %lld\n", (long long)(e.nnzPtriu + e.nnzA));
+  printf("device:   %s (#%d), persistent grid %d x %d threads\n", prop.name, e.device, e.geom.grid, e.geom.block);
+  printf("settings: linear system solver = reduced-KKT Jacobi-PCG on CSR SpMV,\n");
+  printf("          eps_abs = %.1e, eps_rel = %.1e,\n", e.st.eps_abs, e.st.eps_rel);
+  printf("          eps_prim_inf = %.1e, eps_dual_inf = %.1e,\n", e.st.eps_prim_inf, e.st.eps_dual_inf);
+  printf("          rho = %.2e %s, sigma = %.2e, alpha = %.2f, max_iter = %lld\n", e.st.rho,
+         e.st.adaptive_rho ? "(adaptive)" : "", e.st.sigma, e.st.alpha, (long long)e.st.max_iter);
+  printf("          scaling: %s, polish: %s, warm start: %s\n\n", e.st.scaling ? "on" : "off",
+         e.st.polish ? "on" : "off", e.st.warm_start ? "on" : "off");
+}
+
+double spmv_bytes(long long nnz, long long rows, long long cols) {
+  return 12.0 * (double)nnz + 4.0 * (double)(rows + 1) + 8.0 * (double)cols + 8.0 * (double)rows;
+}
+
+c_int upload_vector(Engine &e, double *dst, const c_float *src, long long count) {
+  if (count > 0) CU_OK(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+void osqp_set_default_settings(OSQPSettings *s) {  // src/types.jl:138-143; SURVEY Appendix A
+  memset(s, 0, sizeof(*s));
+  s->rho = 0.1; s->sigma = 1e-6; s->scaling = 10;
+  s->adaptive_rho = 1; s->adaptive_rho_interval = 0; s->adaptive_rho_tolerance = 5; s->adaptive_rho_fraction = 0.4;
+  s->max_iter = 4000; s->eps_abs = 1e-3; s->eps_rel = 1e-3; s->eps_prim_inf = 1e-4; s->eps_dual_inf = 1e-4;
+  s->alpha = 1.6; s->linsys_solver = QDLDL_SOLVER; s->delta = 1e-6; s->polish = 0; s->polish_refine_iter = 3;
+  s->verbose = 1; s->scaled_termination = 0; s->check_termination = 25; s->warm_start = 1; s->time_limit = 0;
+}
+
+const char *osqp_version(void) { return "0.6.2-b200"; }  // src/interface.jl:220
+
+c_int osqp_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+c_int osqp_cleanup(OSQPWorkspace *work) {  // src/interface.jl:224-229 -- NULL and finalizer-thread safe
+  if (work) destroy(E(work));
+  return 0;
+}
+
+c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings *settings) {
+  if (workp) *workp = nullptr;
+  if (!workp) return 1;
+  if (validate_data(data)) return 1;
+  if (validate_settings(settings)) return 1;
+  const double t0 = now_s();
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    fprintf(stderr, "ERROR in osqp_setup: no CUDA device available -- this engine has no CPU fallback\n");
+    return 10;
+  }
+  Engine *ep = new Engine();
+  Engine &e = *ep;
+  memset(&e.prof, 0, sizeof(e.prof));
+  int cur = 0;
+  cudaGetDevice(&cur);
+  e.device = env_int("OSQP_B200_DEVICE", cur);
+  struct Fail {
+    Engine *p;
+    ~Fail() { if (p) destroy(p); }
+  } fail{ep};
+  DeviceGuard guard(e.device);
+  if (!guard.ok) { fprintf(stderr, "ERROR in osqp_setup: cannot select CUDA device %d\n", e.device); return 11; }
+  CU_OK(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+  CU_OK(cudaEventCreate(&e.ev0));
+  CU_OK(cudaEventCreate(&e.ev1));
+  CU_OK(cudaEventCreate(&e.ev2));
+  e.st = *settings;
+  e.pcg_rel_tol = env_double("OSQP_B200_PCG_TOL", e.pcg_rel_tol);
+  e.pcg_abs_tol = env_double("OSQP_B200_PCG_ABS_TOL", e.pcg_abs_tol);
+  e.refresh_every = env_int("OSQP_B200_REFRESH_EVERY", e.refresh_every);
+  e.polish_penalty = env_double("OSQP_B200_POLISH_PENALTY", e.polish_penalty);
+  const int n = (int)data->n, m = (int)data->m;
+  e.pcg_max_iter = env_int("OSQP_B200_PCG_MAX_ITER", std::max(20, std::min(10 * n, 2000)));
+  DevPtrs &d = e.d;
+  d.n = n;
+  d.m = m;
+  const csc *Pc = data->P, *Ac = data->A;
+  const long long nnzA = Ac->p[n], nnzPt = Pc->p[n];
+  e.nnzA = nnzA;
+  e.nnzPtriu = nnzPt;
+
+  // ---- host index work: A' CSR = caller's CSC; A CSR by counting sort; P full symmetric CSR
+  std::vector<int> At_rowptr(n + 1), At_col(nnzA), A_rowptr(m + 1, 0), A_col(nnzA), mapA(nnzA);
+  std::vector<double> A_val(nnzA);
+  for (int j = 0; j <= n; j++) At_rowptr[j] = (int)Ac->p[j];
+  for (long long k = 0; k < nnzA; k++) {
+    const c_int r = Ac->i[k];
+    if (r < 0 || r >= m) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in A\n"); return 1; }
+    At_col[k] = (int)r;
+    A_rowptr[r + 1]++;
+  }
+  for (int i = 0; i < m; i++) A_rowptr[i + 1] += A_rowptr[i];
+  {
+    std::vector<int> w(A_rowptr.begin(), A_rowptr.end() - 1);
+    for (int j = 0; j < n; j++)
+      for (c_int k = Ac->p[j]; k < Ac->p[j + 1]; k++) {
+        const int pos = w[Ac->i[k]]++;
+        A_col[pos] = j;
+        A_val[pos] = Ac->x[k];
+        mapA[k] = pos;
+      }
+  }
+  std::vector<int> P_rowptr(n + 1, 0), mapP1(nnzPt), mapP2(nnzPt);
+  for (int j = 0; j < n; j++)
+    for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
+      const c_int i = Pc->i[k];
+      if (i < 0 || i >= n) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in P\n"); return 1; }
+      P_rowptr[i + 1]++;
+      if (i != j) P_rowptr[j + 1]++;
+    }
+  for (int j = 0; j < n; j++) P_rowptr[j + 1] += P_rowptr[j];
+  const long long nnzP = P_rowptr[n];
+  std::vector<int> P_col(nnzP);
+  std::vector<double> P_val(nnzP);
+  {
+    std::vector<int> w(P_rowptr.begin(), P_rowptr.end() - 1);
+    for (int j = 0; j < n; j++)
+      for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
+        const int i = (int)Pc->i[k];
+        int pos = w[i]++;
+        P_col[pos] = j;
+        P_val[pos] = Pc->x[k];
+        mapP1[k] = pos;
+        if (i != j) {
+          pos = w[j]++;
+          P_col[pos] = i;
+          P_val[pos] = Pc->x[k];
+          mapP2[k] = pos;
+        } else {
+          mapP2[k] = -1;
+        }
+      }
+  }
+
+  // ---- launch geometry
+  cudaDeviceProp prop;
+  CU_OK(cudaGetDeviceProperties(&prop, e.device));
+  e.geom.block = env_int("OSQP_B200_BLOCK", 1024);
+  const int per_sm = max_coop_blocks_per_sm(e.geom.block);
+  if (per_sm <= 0) {
+    fprintf(stderr, "ERROR in osqp_setup: the sm_100a kernels cannot run on device %d (%s, sm_%d%d)\n", e.device,
+            prop.name, prop.major, prop.minor);
+    return 12;
+  }
+  const int max_grid = std::min(kMaxBlocks, prop.multiProcessorCount * std::min(per_sm, env_int("OSQP_B200_BLOCKS_PER_SM", 1)));
+  const long long work = 2 * nnzA + nnzP + 4LL * (n + m);
+  long long want = (work + 32767) / 32768;
+  int grid = (int)std::max(1LL, std::min<long long>(want, max_grid));
+  grid = env_int("OSQP_B200_GRID", grid);
+  e.geom.grid = std::max(1, std::min(grid, max_grid));
+  d.A.rows = m; d.A.cols = n; d.A.nnz = nnzA;
+  d.At.rows = n; d.At.cols = m; d.At.nnz = nnzA;
+  d.P.rows = n; d.P.cols = n; d.P.nnz = nnzP;
+  d.A.lanes = pow2_lanes(m > 0 ? (double)nnzA / m : 1.0);
+  d.At.lanes = d.P.lanes = pow2_lanes((double)(nnzA + nnzP) / n);
+  if (d.A.lanes > e.geom.block) d.A.lanes = e.geom.block;
+
+  // ---- device memory
+  CU_OK(dalloc(e, &d.A.rowptr, (size_t)m + 1)); CU_OK(dalloc(e, &d.A.col, nnzA));
+  CU_OK(dalloc(e, &d.A.val, nnzA)); CU_OK(dalloc(e, &d.A.val0, nnzA));
+  CU_OK(dalloc(e, &d.At.rowptr, (size_t)n + 1)); CU_OK(dalloc(e, &d.At.col, nnzA));
+  CU_OK(dalloc(e, &d.At.val, nnzA)); CU_OK(dalloc(e, &d.At.val0, nnzA));
+  CU_OK(dalloc(e, &d.P.rowptr, (size_t)n + 1)); CU_OK(dalloc(e, &d.P.col, nnzP));
+  CU_OK(dalloc(e, &d.P.val, nnzP)); CU_OK(dalloc(e, &d.P.val0, nnzP));
+  double **nvecs[] = {&d.q, &d.q0, &d.Pdiag, &d.D, &d.Dinv, &d.dtmp, &d.x, &d.xt, &d.dx, &d.r, &d.b, &d.uu,
+                      &d.p, &d.s, &d.w, &d.Minv, &d.pol_x, &d.pol_rhs, &d.sol_x};
+  for (double **p : nvecs) CU_OK(dalloc(e, p, n));
+  double **mvecs[] = {&d.l, &d.u, &d.l0, &d.u0, &d.rho_vec, &d.rho_inv, &d.E, &d.Einv, &d.etmp, &d.z, &d.y, &d.zt,
+                      &d.dy, &d.wv, &d.t, &d.tr, &d.Ap, &d.pol_y, &d.pol_z, &d.pol_rho, &d.pol_b, &d.sol_y};
+  for (double **p : mvecs) CU_OK(dalloc(e, p, m));
+  CU_OK(dalloc(e, &d.ctype, m));
+  CU_OK(dalloc(e, &d.m_start, e.geom.grid + 1));
+  CU_OK(dalloc(e, &d.n_start, e.geom.grid + 1));
+  CU_OK(dalloc(e, &d.bar, 2));
+  CU_OK(dalloc(e, &d.red, (size_t)2 * kRedSlots * e.geom.grid));
+  CU_OK(dalloc(e, &d.state, 1));
+  CU_OK(dalloc(e, &d.info, 1));
+  CU_OK(dalloc(e, &e.d_pol, 1));
+  CU_OK(dalloc(e, &e.mapA, nnzA));
+  CU_OK(dalloc(e, &e.mapP1, nnzPt));
+  CU_OK(dalloc(e, &e.mapP2, nnzPt));
+  CU_OK(halloc(e, &e.h_sol_x, n)); CU_OK(halloc(e, &e.h_sol_y, m));
+  CU_OK(halloc(e, &e.h_dx, n)); CU_OK(halloc(e, &e.h_dy, m));
+  CU_OK(halloc(e, &e.h_info, 1)); CU_OK(halloc(e, &e.h_pol, 1)); CU_OK(halloc(e, &e.h_state, 1));
+
+  // ---- uploads (the caller's buffers may be freed right after we return: everything is copied now)
+#define H2D(dst, src, count, T) \
+  if ((count) > 0) CU_OK(cudaMemcpyAsync(dst, src, (size_t)(count) * sizeof(T), cudaMemcpyHostToDevice, e.stream))
+  H2D(d.A.rowptr, A_rowptr.data(), m + 1, int); H2D(d.A.col, A_col.data(), nnzA, int);
+  H2D(d.A.val0, A_val.data(), nnzA, double);
+  H2D(d.At.rowptr, At_rowptr.data(), n + 1, int); H2D(d.At.col, At_col.data(), nnzA, int);
+  H2D(d.At.val0, Ac->x, nnzA, double);
+  H2D(d.P.rowptr, P_rowptr.data(), n + 1, int); H2D(d.P.col, P_col.data(), nnzP, int);
+  H2D(d.P.val0, P_val.data(), nnzP, double);
+  H2D(d.q0, data->q, n, double); H2D(d.l0, data->l, m, double); H2D(d.u0, data->u, m, double);
+  H2D(e.mapA, mapA.data(), nnzA, int); H2D(e.mapP1, mapP1.data(), nnzPt, int); H2D(e.mapP2, mapP2.data(), nnzPt, int);
+#undef H2D
+  e.l0.assign(data->l, data->l + m);
+  e.u0.assign(data->u, data->u + m);
+  {
+    c_int rc = upload_partition(e, A_rowptr, At_rowptr, P_rowptr);
+    if (rc) return rc;
+  }
+
+  // ---- state, scaling (a2), rho vector (a3), preconditioner, convexity probe
+  e.st.rho = std::min(std::max(e.st.rho, kRhoMin), kRhoMax);
+  memset(e.h_state, 0, sizeof(DevState));
+  e.h_state->rho = e.st.rho;
+  e.h_state->c = 1.0;
+  e.h_state->cinv = 1.0;
+  e.h_state->adaptive_interval = e.st.adaptive_rho_interval;
+  e.h_state->needs_refresh = 1;
+  { c_int rc = push_state(e); if (rc) return rc; }
+  { c_int rc = rescale_and_refresh(e, true); if (rc) return rc; }
+  CU_OK(launch_pd_probe(d, e.geom, e.st.sigma, std::min(n, env_int("OSQP_B200_PD_PROBE_ITERS", 200)), e.stream));
+  e.prof.launches += 1;
+  { c_int rc = pull_state(e); if (rc) return rc; }
+  if (e.h_state->pd_check_failed) {
+    fprintf(stderr, "ERROR in osqp_setup: P + sigma*I is not positive definite (the problem seems to be non-convex)\n");
+    return 7;
+  }
+
+  memset(&e.info, 0, sizeof(e.info));
+  update_status(e.info, OSQP_UNSOLVED);
+  e.info.rho_estimate = e.st.rho;
+  e.first_run = true;
+  e.prof.device = e.device;
+  e.prof.grid = e.geom.grid;
+  e.prof.block = e.geom.block;
+  e.prof.lanes_A = d.A.lanes;
+  e.prof.lanes_N = d.At.lanes;
+  e.prof.nnz_A = nnzA;
+  e.prof.nnz_P_full = nnzP;
+  e.prof.spmv_bytes_A = spmv_bytes(nnzA, m, n);
+  e.prof.spmv_bytes_At = spmv_bytes(nnzA, n, m);
+  e.prof.spmv_bytes_P = spmv_bytes(nnzP, n, n);
+  publish(e);
+  e.info.setup_time = now_s() - t0;
+  if (e.st.verbose) print_setup_header(e);
+  fail.p = nullptr;
+  *workp = &e.pub;
+  return 0;
+}
+
+c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
+  if (!work) { fprintf(stderr, "ERROR in osqp_solve: workspace not initialized\n"); return 1; }
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  if (e.clear_update_time) e.info.update_time = 0.0;
+  const double t0 = now_s();
+  SolveCfg c;
+  memset(&c, 0, sizeof(c));
+  c.sigma = e.st.sigma; c.alpha = e.st.alpha;
+  c.eps_abs = e.st.eps_abs; c.eps_rel = e.st.eps_rel;
+  c.eps_prim_inf = e.st.eps_prim_inf; c.eps_dual_inf = e.st.eps_dual_inf;
+  c.max_iter = e.st.max_iter; c.check_termination = e.st.check_termination;
+  c.scaling = e.st.scaling != 0; c.scaled_termination = (int)e.st.scaled_termination;
+  c.adaptive_rho = (int)e.st.adaptive_rho; c.adaptive_rho_tolerance = e.st.adaptive_rho_tolerance;
+  c.adaptive_time_s = e.st.adaptive_rho_fraction * e.info.setup_time;
+  c.warm_start = (int)e.st.warm_start; c.verbose = (int)e.st.verbose;
+  const double base = e.first_run ? e.info.setup_time : e.info.update_time;
+  c.time_limit_s = e.st.time_limit > 0 ? e.st.time_limit - base : -1e30;
+  // Inner accuracy follows the outer tolerance: the oracle study in DESIGN.md shows the ADMM iterates
+  // track the exact-solve trajectory (same iteration count, errors << eps) at 1e-2 * eps.
+  c.pcg_rel_tol = e.pcg_rel_tol > 0 ? e.pcg_rel_tol
+                                    : std::max(1e-13, std::min(1e-7, 0.01 * std::max(e.st.eps_abs, e.st.eps_rel)));
+  c.pcg_abs_tol = e.pcg_abs_tol; c.pcg_max_iter = e.pcg_max_iter;
+  c.refresh_every = e.refresh_every;
+  if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
+
+  CU_OK(cudaEventRecord(e.ev0, e.stream));
+  CU_OK(launch_solve(e.d, c, e.geom, e.stream));
+  CU_OK(cudaEventRecord(e.ev1, e.stream));
+  e.prof.launches += 1;
+  const int n = e.d.n, m = e.d.m;
+  CU_OK(cudaMemcpyAsync(e.h_info, e.d.info, sizeof(DevInfo), cudaMemcpyDeviceToHost, e.stream));
+  CU_OK(cudaMemcpyAsync(e.h_sol_x, e.d.sol_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  if (m > 0) CU_OK(cudaMemcpyAsync(e.h_sol_y, e.d.sol_y, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  CU_OK(cudaStreamSynchronize(e.stream));
+  const DevInfo &I = *e.h_info;
+  e.info.iter = I.iter;
+  update_status(e.info, I.status_val);
+  e.info.obj_val = I.obj_val;
+  e.info.pri_res = I.pri_res;
+  e.info.dua_res = I.dua_res;
+  e.info.rho_updates = I.rho_updates;
+  e.info.rho_estimate = I.rho_estimate;
+  e.st.rho = I.rho;
+  e.st.adaptive_rho_interval = I.adaptive_interval;
+  e.h_state->rho = I.rho;
+  e.h_state->rho_updates = I.rho_updates;
+  e.h_state->adaptive_interval = I.adaptive_interval;
+  const c_int sv = I.status_val;
+  if (sv == OSQP_PRIMAL_INFEASIBLE || sv == OSQP_PRIMAL_INFEASIBLE_INACCURATE) {
+    if (m > 0) CU_OK(cudaMemcpyAsync(e.h_dy, e.d.dy, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    CU_OK(cudaStreamSynchronize(e.stream));
+  } else if (sv == OSQP_DUAL_INFEASIBLE || sv == OSQP_DUAL_INFEASIBLE_INACCURATE) {
+    CU_OK(cudaMemcpyAsync(e.h_dx, e.d.dx, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    CU_OK(cudaStreamSynchronize(e.stream));
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  e.prof.kernel_ms = ms;
+  e.prof.polish_ms = 0;
+  e.prof.admm_iters = I.cg_solves;
+  e.prof.pcg_iters = I.cg_iters;
+  e.prof.info_evals = I.checks;
+  e.prof.refreshes = I.refreshes;
+  {
+    // algorithmic bytes of this launch (DESIGN.md "bytes model"): matrix streams + dense vector passes
+    const double bA = e.prof.spmv_bytes_A, bAt = e.prof.spmv_bytes_At, bP = e.prof.spmv_bytes_P;
+    const double k = (double)I.cg_iters, it = (double)I.cg_solves, ck = (double)I.checks, rf = (double)I.refreshes;
+    const double vn = 8.0 * n, vm = 8.0 * m;
+    e.prof.alg_bytes = k * (bA + bAt + bP + 11 * vn + 5 * vm) + it * (bAt + 6 * vn + 12 * vm + 4 * vn) +
+                       rf * (bA + bP) + ck * (bA + bAt + bP);
+  }
+  if (e.st.verbose) {
+    for (long long r = 0; r < I.log_rows; r++)
+      printf("%4lld  %11.4e  %9.2e  %9.2e  %9.2e  %9.2es\n", (long long)I.log[r][0], I.log[r][1], I.log[r][2],
+             I.log[r][3], I.log[r][4], I.log[r][5]);
+    if (I.log_rows == 0 || (long long)I.log[I.log_rows - 1][0] != I.iter)
+      printf("%4lld  %11.4e  %9.2e  %9.2e  %9.2e  %9.2es\n", (long long)I.iter, I.obj_val, I.pri_res, I.dua_res,
+             I.rho, I.elapsed_s);
+  }
+  e.info.solve_time = now_s() - t0;
+
+  // ---- polish (a12)
+  if (e.st.polish && sv == OSQP_SOLVED) {
+    const double tp = now_s();
+    PolishCfg pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.delta = e.st.delta;
+    pc.penalty = e.polish_penalty;
+    pc.refine_iter = 1 + 2 * (int)e.st.polish_refine_iter;
+    pc.pcg_rel_tol = 1e-13;
+    pc.pcg_max_iter = std::max(50, std::min(20 * n, 20000));
+    pc.scaling = c.scaling;
+    pc.scaled_termination = c.scaled_termination;
+    CU_OK(launch_polish(e.d, pc, c, e.d_pol, e.geom, e.stream));
+    CU_OK(cudaEventRecord(e.ev2, e.stream));
+    e.prof.launches += 1;
+    CU_OK(cudaMemcpyAsync(e.h_pol, e.d_pol, sizeof(PolishOut), cudaMemcpyDeviceToHost, e.stream));
+    CU_OK(cudaMemcpyAsync(e.h_sol_x, e.d.sol_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    if (m > 0) CU_OK(cudaMemcpyAsync(e.h_sol_y, e.d.sol_y, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    CU_OK(cudaStreamSynchronize(e.stream));
+    cudaEventElapsedTime(&ms, e.ev1, e.ev2);
+    e.prof.polish_ms = ms;
+    if (e.h_pol->success) {
+      e.info.obj_val = e.h_pol->obj_val;
+      e.info.pri_res = e.h_pol->pri_res;
+      e.info.dua_res = e.h_pol->dua_res;
+      e.info.status_polish = 1;
+    } else {
+      e.info.status_polish = -1;
+    }
+    e.info.polish_time = now_s() - tp;
+    if (e.st.verbose && e.h_pol->success)
+      printf("plsh  %11.4e  %9.2e  %9.2e   --------  %9.2es\n", e.info.obj_val, e.info.pri_res, e.info.dua_res,
+             e.info.polish_time);
+  }
+  e.info.run_time = base + e.info.solve_time + e.info.polish_time;
+  e.first_run = false;
+  e.clear_update_time = true;
+  e.pub.first_run = 0;
+  if (e.st.verbose) {
+    printf("\nstatus:               %s\n", e.info.status);
+    if (e.st.polish && sv == OSQP_SOLVED)
+      printf("solution polish:      %s\n", e.info.status_polish == 1 ? "successful" : "unsuccessful");
+    printf("number of iterations: %lld\n", (long long)e.info.iter);
+    if (sv == OSQP_SOLVED || sv == OSQP_SOLVED_INACCURATE) printf("optimal objective:    %.4f\n", e.info.obj_val);
+    printf("run time:             %.2es\n", e.info.run_time);
+    printf("optimal rho estimate: %.2e\n\n", e.info.rho_estimate);
+  }
+  return 0;
+}
+
+// ---- updates (a13)
+c_int osqp_update_lin_cost(OSQPWorkspace *work, const c_float *q_new) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  { c_int rc = upload_vector(e, e.d.q0, q_new, e.d.n); if (rc) return rc; }
+  CU_OK(launch_scale_vectors(e.d, 1, 0, e.stream));
+  e.prof.launches += 1;
+  CU_OK(cudaStreamSynchronize(e.stream));  // q_new is caller-owned
+  reset_info(e);
+  { c_int rc = push_state(e); if (rc) return rc; }
+  e.info.update_time += now_s() - t0;
+  return 0;
+}
+
+static c_int bounds_changed(Engine &e) {
+  CU_OK(launch_scale_vectors(e.d, 0, 1, e.stream));
+  CU_OK(launch_set_rho_vec(e.d, e.st.rho, 1, e.stream));
+  CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
+  e.prof.launches += 3;
+  CU_OK(cudaStreamSynchronize(e.stream));
+  reset_info(e);
+  e.h_state->needs_refresh = 1;
+  return push_state(e);
+}
+
+c_int osqp_update_bounds(OSQPWorkspace *work, const c_float *l_new, const c_float *u_new) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  const int m = e.d.m;
+  for (int i = 0; i < m; i++)
+    if (l_new[i] > u_new[i]) {
+      fprintf(stderr, "ERROR in osqp_update_bounds: lower bound must be lower than or equal to upper bound\n");
+      return 1;
+    }
+  e.l0.assign(l_new, l_new + m);
+  e.u0.assign(u_new, u_new + m);
+  { c_int rc = upload_vector(e, e.d.l0, l_new, m); if (rc) return rc; }
+  { c_int rc = upload_vector(e, e.d.u0, u_new, m); if (rc) return rc; }
+  c_int rc = bounds_changed(e);
+  e.info.update_time += now_s() - t0;
+  return rc;
+}
+c_int osqp_update_lower_bound(OSQPWorkspace *work, const c_float *l_new) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  const int m = e.d.m;
+  for (int i = 0; i < m; i++)
+    if (l_new[i] > e.u0[i]) {
+      fprintf(stderr, "ERROR in osqp_update_lower_bound: upper bound must be greater than or equal to lower bound\n");
+      return 1;
+    }
+  e.l0.assign(l_new, l_new + m);
+  { c_int rc = upload_vector(e, e.d.l0, l_new, m); if (rc) return rc; }
+  c_int rc = bounds_changed(e);
+  e.info.update_time += now_s() - t0;
+  return rc;
+}
+c_int osqp_update_upper_bound(OSQPWorkspace *work, const c_float *u_new) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  const int m = e.d.m;
+  for (int i = 0; i < m; i++)
+    if (e.l0[i] > u_new[i]) {
+      fprintf(stderr, "ERROR in osqp_update_upper_bound: upper bound must be greater than or equal to lower bound\n");
+      return 1;
+    }
+  e.u0.assign(u_new, u_new + m);
+  { c_int rc = upload_vector(e, e.d.u0, u_new, m); if (rc) return rc; }
+  c_int rc = bounds_changed(e);
+  e.info.update_time += now_s() - t0;
+  return rc;
+}
+
+static c_int stage_values(Engine &e, const c_float *vals, const c_int *idx, long long k) {
+  if (k > e.stage_cap) {
+    long long cap = std::max<long long>(k, 1024);
+    CU_OK(dalloc(e, &e.stage_val, cap));
+    CU_OK(dalloc(e, &e.stage_idx, cap));
+    e.stage_cap = cap;
+  }
+  CU_OK(cudaMemcpyAsync(e.stage_val, vals, k * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  if (idx) CU_OK(cudaMemcpyAsync(e.stage_idx, idx, k * sizeof(long long), cudaMemcpyHostToDevice, e.stream));
+  return 0;
+}
+
+static c_int update_PA(Engine &e, const c_float *Px_new, const c_int *Px_idx, c_int P_n, bool doP,
+                       const c_float *Ax_new, const c_int *Ax_idx, c_int A_n, bool doA) {
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  if (doP && Px_idx && P_n > e.nnzPtriu) {
+    fprintf(stderr, "ERROR in osqp_update_P: new number of elements (%lld) greater than elements in P (%lld)\n",
+            (long long)P_n, (long long)e.nnzPtriu);
+    return 1;
+  }
+  if (doA && Ax_idx && A_n > e.nnzA) {
+    fprintf(stderr, "ERROR in osqp_update_A: new number of elements (%lld) greater than elements in A (%lld)\n",
+            (long long)A_n, (long long)e.nnzA);
+    return doP ? 2 : 1;
+  }
+  if (doP) {
+    const long long k = Px_idx ? P_n : e.nnzPtriu;
+    if (Px_idx)
+      for (long long t = 0; t < k; t++)
+        if (Px_idx[t] < 0 || Px_idx[t] >= e.nnzPtriu) { fprintf(stderr, "ERROR in osqp_update_P: index out of range\n"); return 1; }
+    { c_int rc = stage_values(e, Px_new, Px_idx, k); if (rc) return rc; }
+    CU_OK(launch_scatter_values(e.d.P.val0, e.stage_val, Px_idx ? e.stage_idx : nullptr, e.mapP1, k, e.stream));
+    CU_OK(launch_scatter_values(e.d.P.val0, e.stage_val, Px_idx ? e.stage_idx : nullptr, e.mapP2, k, e.stream));
+    e.prof.launches += 2;
+    CU_OK(cudaStreamSynchronize(e.stream));
+  }
+  if (doA) {
+    const long long k = Ax_idx ? A_n : e.nnzA;
+    if (Ax_idx)
+      for (long long t = 0; t < k; t++)
+        if (Ax_idx[t] < 0 || Ax_idx[t] >= e.nnzA) { fprintf(stderr, "ERROR in osqp_update_A: index out of range\n"); return doP ? 2 : 1; }
+    { c_int rc = stage_values(e, Ax_new, Ax_idx, k); if (rc) return rc; }
+    CU_OK(launch_scatter_values(e.d.At.val0, e.stage_val, Ax_idx ? e.stage_idx : nullptr, nullptr, k, e.stream));
+    CU_OK(launch_scatter_values(e.d.A.val0, e.stage_val, Ax_idx ? e.stage_idx : nullptr, e.mapA, k, e.stream));
+    e.prof.launches += 2;
+    CU_OK(cudaStreamSynchronize(e.stream));
+  }
+  // unscale -> overwrite -> scale of libosqp == re-equilibrate the stored originals
+  { c_int rc = rescale_and_refresh(e, false); if (rc) return rc; }
+  CU_OK(launch_pd_probe(e.d, e.geom, e.st.sigma, std::min(e.d.n, env_int("OSQP_B200_PD_PROBE_ITERS", 200)), e.stream));
+  e.prof.launches += 1;
+  { c_int rc = pull_state(e); if (rc) return rc; }
+  reset_info(e);
+  e.h_state->needs_refresh = 1;
+  const int failed = e.h_state->pd_check_failed;
+  e.h_state->pd_check_failed = 0;
+  { c_int rc = push_state(e); if (rc) return rc; }
+  e.info.update_time += now_s() - t0;
+  if (failed) {
+    fprintf(stderr, "ERROR in osqp_update_P/A: new KKT matrix is not quasidefinite\n");
+    return -2;
+  }
+  return 0;
+}
+c_int osqp_update_P(OSQPWorkspace *work, const c_float *Px_new, const c_int *Px_new_idx, c_int P_new_n) {
+  if (!work) return 1;
+  return update_PA(*E(work), Px_new, Px_new_idx, P_new_n, true, nullptr, nullptr, 0, false);
+}
+c_int osqp_update_A(OSQPWorkspace *work, const c_float *Ax_new, const c_int *Ax_new_idx, c_int A_new_n) {
+  if (!work) return 1;
+  return update_PA(*E(work), nullptr, nullptr, 0, false, Ax_new, Ax_new_idx, A_new_n, true);
+}
+c_int osqp_update_P_A(OSQPWorkspace *work, const c_float *Px_new, const c_int *Px_new_idx, c_int P_new_n,
+                      const c_float *Ax_new, const c_int *Ax_new_idx, c_int A_new_n) {
+  if (!work) return 1;
+  return update_PA(*E(work), Px_new, Px_new_idx, P_new_n, true, Ax_new, Ax_new_idx, A_new_n, true);
+}
+
+// ---- warm start (a14)
+static c_int warm(Engine &e, const c_float *x, const c_float *y) {
+  DeviceGuard guard(e.device);
+  if (!e.st.warm_start) e.st.warm_start = 1;
+  // stage in pol_x / pol_y (free outside a polish launch)
+  if (x) { c_int rc = upload_vector(e, e.d.pol_x, x, e.d.n); if (rc) return rc; }
+  if (y) { c_int rc = upload_vector(e, e.d.pol_y, y, e.d.m); if (rc) return rc; }
+  CU_OK(launch_warm_start(e.d, x ? e.d.pol_x : nullptr, y ? e.d.pol_y : nullptr, e.st.scaling != 0, e.stream));
+  e.prof.launches += x ? 2 : 1;
+  CU_OK(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+c_int osqp_warm_start(OSQPWorkspace *work, const c_float *x, const c_float *y) {
+  if (!work) return 1;
+  return warm(*E(work), x, y);
+}
+c_int osqp_warm_start_x(OSQPWorkspace *work, const c_float *x) {
+  if (!work) return 1;
+  return warm(*E(work), x, nullptr);
+}
+c_int osqp_warm_start_y(OSQPWorkspace *work, const c_float *y) {
+  if (!work) return 1;
+  return warm(*E(work), nullptr, y);
+}
+
+// ---- settings (a15)
+#define ENGINE_SETTER(NAME, TYPE, FIELD, BADCOND, MSG)                            \
+  c_int NAME(OSQPWorkspace *work, TYPE v) {                                       \
+    if (!work) return 1;                                                          \
+    if (BADCOND) { fprintf(stderr, "ERROR in " #NAME ": " MSG "\n"); return 1; }  \
+    E(work)->st.FIELD = v;                                                        \
+    return 0;                                                                     \
+  }
+ENGINE_SETTER(osqp_update_max_iter, c_int, max_iter, v <= 0, "max_iter must be positive")
+ENGINE_SETTER(osqp_update_eps_abs, c_float, eps_abs, v < 0, "eps_abs must be nonnegative")
+ENGINE_SETTER(osqp_update_eps_rel, c_float, eps_rel, v < 0, "eps_rel must be nonnegative")
+ENGINE_SETTER(osqp_update_eps_prim_inf, c_float, eps_prim_inf, v < 0, "eps_prim_inf must be nonnegative")
+ENGINE_SETTER(osqp_update_eps_dual_inf, c_float, eps_dual_inf, v < 0, "eps_dual_inf must be nonnegative")
+ENGINE_SETTER(osqp_update_alpha, c_float, alpha, (v <= 0 || v >= 2), "alpha must be between 0 and 2")
+ENGINE_SETTER(osqp_update_delta, c_float, delta, v <= 0, "delta must be positive")
+ENGINE_SETTER(osqp_update_polish_refine_iter, c_int, polish_refine_iter, v < 0, "polish_refine_iter must be nonnegative")
+ENGINE_SETTER(osqp_update_verbose, c_int, verbose, (v != 0 && v != 1), "verbose should be either 0 or 1")
+ENGINE_SETTER(osqp_update_scaled_termination, c_int, scaled_termination, (v != 0 && v != 1), "scaled_termination should be either 0 or 1")
+ENGINE_SETTER(osqp_update_check_termination, c_int, check_termination, v < 0, "check_termination should be nonnegative")
+ENGINE_SETTER(osqp_update_warm_start, c_int, warm_start, (v != 0 && v != 1), "warm_start should be either 0 or 1")
+ENGINE_SETTER(osqp_update_time_limit, c_float, time_limit, v < 0, "time_limit must be nonnegative")
+
+c_int osqp_update_polish(OSQPWorkspace *work, c_int v) {
+  if (!work) return 1;
+  if (v != 0 && v != 1) { fprintf(stderr, "ERROR in osqp_update_polish: polish should be either 0 or 1\n"); return 1; }
+  E(work)->st.polish = v;
+  E(work)->info.polish_time = 0.0;
+  return 0;
+}
+
+c_int osqp_update_rho(OSQPWorkspace *work, c_float rho_new) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  if (rho_new <= 0) { fprintf(stderr, "ERROR in osqp_update_rho: rho must be positive\n"); return 1; }
+  DeviceGuard guard(e.device);
+  begin_update(e);
+  const double t0 = now_s();
+  e.st.rho = std::min(std::max(rho_new, kRhoMin), kRhoMax);
+  e.h_state->rho = e.st.rho;
+  e.h_state->needs_refresh = 1;
+  { c_int rc = push_state(e); if (rc) return rc; }
+  CU_OK(launch_apply_rho(e.d, e.st.rho, e.stream));
+  CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
+  e.prof.launches += 2;
+  CU_OK(cudaStreamSynchronize(e.stream));
+  e.info.update_time += now_s() - t0;
+  return 0;
+}
+
+// ---- engine extensions (include/osqp_b200.h)
+c_int osqp_b200_get_profile(const OSQPWorkspace *work, OSQPB200Profile *out) {
+  if (!work || !out) return 1;
+  *out = E(work)->prof;
+  return 0;
+}
+
+c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float rel_tol, c_float abs_tol, c_int max_iter, c_int refresh_every) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  if (rel_tol > 0) e.pcg_rel_tol = rel_tol;
+  if (abs_tol > 0) e.pcg_abs_tol = abs_tol;
+  if (max_iter > 0) e.pcg_max_iter = (int)max_iter;
+  if (refresh_every >= 0) e.refresh_every = (int)refresh_every;
+  return 0;
+}
+
+c_int osqp_b200_spmv(OSQPWorkspace *work, c_int which, const c_float *in_host, c_float *out_host, c_int reps,
+                     c_float *ms_per_rep) {
+  if (!work || which < 0 || which > 2 || reps < 1) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  const int n = e.d.n, m = e.d.m;
+  const int in_len = (which == 1) ? m : n, out_len = (which == 0) ? m : n;
+  // scratch: PCG vectors are free between solves (uu/w are n, t/tr are m)
+  double *din = (which == 1) ? e.d.tr : e.d.uu;
+  double *dout = (which == 0) ? e.d.t : e.d.w;
+  { c_int rc = upload_vector(e, din, in_host, in_len); if (rc) return rc; }
+  CU_OK(launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream));  // warm-up
+  CU_OK(cudaEventRecord(e.ev0, e.stream));
+  for (c_int r = 0; r < reps; r++) CU_OK(launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream));
+  CU_OK(cudaEventRecord(e.ev1, e.stream));
+  e.prof.launches += (c_int)reps + 1;
+  if (out_host && out_len > 0)
+    CU_OK(cudaMemcpyAsync(out_host, dout, (size_t)out_len * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  CU_OK(cudaStreamSynchronize(e.stream));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e.ev0, e.ev1);
+  if (ms_per_rep) *ms_per_rep = (double)ms / (double)reps;
+  e.h_state->needs_refresh = 1;
+  return 0;
+}
+
+c_int osqp_b200_get_scaling(OSQPWorkspace *work, c_float *D, c_float *Ev, c_float *c) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  if (D) CU_OK(cudaMemcpyAsync(D, e.d.D, (size_t)e.d.n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  if (Ev && e.d.m > 0) CU_OK(cudaMemcpyAsync(Ev, e.d.E, (size_t)e.d.m * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+  { c_int rc = pull_state(e); if (rc) return rc; }
+  if (c) *c = e.h_state->c;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,210 @@
+"""CUDA engine vs CPU oracle on the same seeded inputs (GPU tests; all calls go through the C ABI).
+
+Tolerances (north_star): same status; (x*, y*) within the solver's own eps_abs/eps_rel; iteration
+count within +-1 when rho is held fixed.  SpMV: relative 1e-13 (fp64, different summation order).
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from reference_cases import random_qp, sprandn
+
+pytestmark = pytest.mark.gpu
+
+FIXED_RHO = dict(verbose=False, adaptive_rho=False, check_termination=1, max_iter=20000, polish=False)
+
+
+def solve_both(pkg, engine_lib, oracle_lib, prob, opts, oracle_pcg=False):
+    """oracle_pcg: use the oracle's reduced-KKT PCG backend at tolerance 1e-12 instead of the direct
+    LDL' (whose fill-in on random patterns makes n > ~2000 take minutes); test_oracle_backends.py
+    shows the two oracle backends give identical iteration counts."""
+    out = {}
+    ora = pkg.load_library(oracle_lib)
+    ora.osqp_oracle_configure.argtypes = [C.c_longlong, C.c_double, C.c_longlong]
+    for name, lib in (("engine", engine_lib), ("oracle", oracle_lib)):
+        if name == "oracle" and oracle_pcg:
+            ora.osqp_oracle_configure(1, 1e-12, 0)
+        try:
+            mdl = pkg.Model(lib=lib)
+            mdl.setup(**prob, **opts)
+        finally:
+            ora.osqp_oracle_configure(0, 1e-9, 0)
+        out[name] = (mdl, mdl.solve())
+    return out
+
+
+def assert_parity(e, o, eps, iter_tol=1):
+    assert e.info.status == o.info.status, (e.info.status, o.info.status)
+    assert abs(e.info.iter - o.info.iter) <= iter_tol, (e.info.iter, o.info.iter)
+    sx = eps * (1.0 + np.max(np.abs(o.x)))
+    sy = eps * (1.0 + np.max(np.abs(o.y))) if o.y.size else 0.0
+    assert np.max(np.abs(e.x - o.x)) <= sx, (np.max(np.abs(e.x - o.x)), sx)
+    if o.y.size:
+        assert np.max(np.abs(e.y - o.y)) <= sy, (np.max(np.abs(e.y - o.y)), sy)
+    assert abs(e.info.obj_val - o.info.obj_val) <= 10 * eps * (1.0 + abs(o.info.obj_val))
+
+
+@pytest.mark.parametrize("n,m,density,seed,eps,oracle_pcg", [
+    (50, 80, 0.2, 1, 1e-4, False), (50, 80, 0.2, 1, 1e-7, False),
+    (300, 500, 0.05, 2, 1e-4, False), (300, 500, 0.05, 2, 1e-7, False),
+    (2000, 4000, 0.005, 3, 1e-4, False), (2000, 4000, 0.005, 3, 1e-7, True),
+    (5000, 10000, 0.002, 4, 1e-4, True), (20000, 40000, 0.0015, 5, 1e-4, True)])
+def test_random_qp_fixed_rho(pkg, engine_lib, oracle_lib, n, m, density, seed, eps, oracle_pcg):
+    prob = random_qp(n, m, density, seed)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, dict(FIXED_RHO, eps_abs=eps, eps_rel=eps), oracle_pcg)
+    assert_parity(r["engine"][1], r["oracle"][1], eps)
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_random_qp_adaptive_rho_fixed_interval(pkg, engine_lib, oracle_lib, seed):
+    # adaptive_rho_interval=25 is what the reference's own tests use "for deterministic behavior"
+    # (test/MOI_wrapper.jl:41-49)
+    prob = random_qp(1000, 2000, 0.01, seed)
+    opts = dict(verbose=False, eps_abs=1e-5, eps_rel=1e-5, adaptive_rho_interval=25, max_iter=20000)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, opts)
+    e, o = r["engine"][1], r["oracle"][1]
+    assert e.info.rho_updates == o.info.rho_updates
+    assert abs(e.info.rho_estimate - o.info.rho_estimate) <= 1e-3 * o.info.rho_estimate
+    assert_parity(e, o, 1e-5, iter_tol=25)
+
+
+def test_equality_and_loose_rows(pkg, engine_lib, oracle_lib):
+    # mixes the three rho classes of set_rho_vec: equality (1e3 rho), two-sided, loose (1e-6)
+    rng = np.random.default_rng(9)
+    prob = random_qp(400, 600, 0.03, 9)
+    l, u = prob["l"].copy(), prob["u"].copy()
+    eq = rng.random(600) < 0.2
+    u[eq] = l[eq]
+    loose = (~eq) & (rng.random(600) < 0.2)
+    l[loose], u[loose] = -np.inf, np.inf
+    onesided = (~eq) & (~loose) & (rng.random(600) < 0.3)
+    u[onesided] = np.inf
+    prob.update(l=l, u=u)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, dict(FIXED_RHO, eps_abs=1e-6, eps_rel=1e-6))
+    assert_parity(r["engine"][1], r["oracle"][1], 1e-6, iter_tol=2)
+
+
+def test_no_scaling_and_scaled_termination(pkg, engine_lib, oracle_lib):
+    prob = random_qp(200, 300, 0.05, 12)
+    for extra in (dict(scaling=0), dict(scaled_termination=1), dict(alpha=1.0), dict(sigma=1e-3, rho=1.0)):
+        r = solve_both(pkg, engine_lib, oracle_lib, prob, dict(FIXED_RHO, eps_abs=1e-6, eps_rel=1e-6, **extra))
+        assert_parity(r["engine"][1], r["oracle"][1], 1e-6)
+
+
+def test_scaling_vectors_match_oracle(pkg, engine_lib, oracle_lib):
+    prob = random_qp(500, 700, 0.02, 21)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, dict(FIXED_RHO, eps_abs=1e-3, eps_rel=1e-3))
+    n, m = 500, 700
+    eng = pkg.load_library(engine_lib)
+    ora = pkg.load_library(oracle_lib)
+    fp = C.POINTER(C.c_double)
+    De, Ee, ce = np.zeros(n), np.zeros(m), C.c_double()
+    Do, Eo, co = np.zeros(n), np.zeros(m), C.c_double()
+    eng.osqp_b200_get_scaling.restype = C.c_longlong
+    assert eng.osqp_b200_get_scaling(r["engine"][0].workspace, De.ctypes.data_as(fp), Ee.ctypes.data_as(fp), C.byref(ce)) == 0
+    ora.osqp_oracle_get_scaling(r["oracle"][0].workspace, Do.ctypes.data_as(fp), Eo.ctypes.data_as(fp), C.byref(co))
+    # same multiplication order on both sides; only the mean in the cost scaling is summed differently
+    assert np.allclose(De, Do, rtol=1e-12, atol=0)
+    assert np.allclose(Ee, Eo, rtol=1e-12, atol=0)
+    assert abs(ce.value - co.value) <= 1e-12 * co.value
+
+
+@pytest.mark.parametrize("which", [0, 1, 2])
+def test_spmv_kernels_match_oracle(pkg, engine_lib, oracle_lib, which):
+    n, m = 3000, 5000
+    prob = random_qp(n, m, 0.004, 33)
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, verbose=False, scaling=0, sigma=1e-6)  # scaling off => resident matrices == inputs
+    eng = pkg.load_library(engine_lib)
+    ora = pkg.load_library(oracle_lib)
+    fp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(4)
+    vin = rng.standard_normal(m if which == 1 else n)
+    out = np.zeros(m if which == 0 else n)
+    ms = C.c_double()
+    eng.osqp_b200_spmv.restype = C.c_longlong
+    rc = eng.osqp_b200_spmv(mdl.workspace, C.c_longlong(which), vin.ctypes.data_as(fp), out.ctypes.data_as(fp),
+                            C.c_longlong(3), C.byref(ms))
+    assert rc == 0 and ms.value > 0
+    A = pkg.ManagedCcsc(prob["A"])
+    ref = np.zeros_like(out)
+    if which == 0:
+        ca = A.ccsc()
+        ora.osqp_oracle_mat_vec(C.byref(ca), vin.ctypes.data_as(fp), ref.ctypes.data_as(fp), C.c_longlong(0))
+        scale = abs(prob["A"]) @ np.abs(vin)
+    elif which == 1:
+        ca = A.ccsc()
+        ora.osqp_oracle_mat_vec(C.byref(ca), vin.ctypes.data_as(fp), ref.ctypes.data_as(fp), C.c_longlong(1))
+        scale = abs(prob["A"]).T @ np.abs(vin)
+    else:
+        Pm = pkg.ManagedCcsc(prob["P"])
+        cp = Pm.ccsc()
+        ora.osqp_oracle_mat_vec(C.byref(cp), vin.ctypes.data_as(fp), ref.ctypes.data_as(fp), C.c_longlong(0))
+        ref += 1e-6 * vin
+        scale = abs(prob["P"]) @ np.abs(vin)
+    assert np.all(np.abs(out - ref) <= 1e-13 * (scale + 1.0))
+
+
+def test_updates_and_warm_start_match_oracle(pkg, engine_lib, oracle_lib):
+    # the MOI re-solve path (src/modcaches.jl:166-179): bounds, P, q, A updates then warm-started solve
+    rng = np.random.default_rng(17)
+    prob = random_qp(300, 450, 0.04, 17)
+    opts = dict(FIXED_RHO, eps_abs=1e-6, eps_rel=1e-6)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, opts)
+    Pt = sp.triu(prob["P"], format="csc")
+    newP = Pt.data * (1.0 + 0.1 * rng.random(Pt.data.size))
+    idxA = rng.choice(prob["A"].nnz, size=50, replace=False).astype(np.int64)
+    newA = rng.standard_normal(50)
+    q2 = prob["q"] + 0.3 * rng.standard_normal(300)
+    l2, u2 = prob["l"] - 0.1, prob["u"] + 0.2
+    for name in ("engine", "oracle"):
+        mdl = r[name][0]
+        mdl.update_bounds(l2, u2)
+        mdl.update_P(newP, None)
+        mdl.update_q(q2)
+        mdl.update_A(newA, idxA)
+    e, o = r["engine"][0].solve(), r["oracle"][0].solve()
+    assert_parity(e, o, 1e-6, iter_tol=2)
+    x0, y0 = rng.standard_normal(300), rng.standard_normal(450)
+    for name in ("engine", "oracle"):
+        r[name][0].warm_start(x=x0, y=y0)
+    e, o = r["engine"][0].solve(), r["oracle"][0].solve()
+    assert_parity(e, o, 1e-6, iter_tol=2)
+
+
+def test_resolve_is_deterministic(pkg, engine_lib):
+    prob = random_qp(800, 1200, 0.01, 23)
+    opts = dict(FIXED_RHO, eps_abs=1e-6, eps_rel=1e-6)
+    a = pkg.Model(lib=engine_lib)
+    a.setup(**prob, **opts)
+    ra = a.solve()
+    b = pkg.Model(lib=engine_lib)
+    b.setup(**prob, **opts)
+    rb = b.solve()
+    assert ra.info.iter == rb.info.iter
+    assert np.array_equal(ra.x, rb.x) and np.array_equal(ra.y, rb.y)
+
+
+def test_kkt_optimality_at_scale(pkg, engine_lib):
+    # size-independent property: the returned (x*, y*) satisfies the unscaled KKT conditions to eps
+    n, m = 20000, 40000
+    prob = random_qp(n, m, 0.0015, 41)
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, verbose=False, eps_abs=1e-5, eps_rel=1e-5, adaptive_rho_interval=25, max_iter=20000)
+    r = mdl.solve()
+    assert r.info.status == "Solved"
+    P, A, q, l, u = prob["P"], prob["A"], prob["q"], prob["l"], prob["u"]
+    Ax = A @ r.x
+    z = np.clip(Ax, l, u)
+    pri = np.max(np.abs(Ax - z))
+    dua = np.max(np.abs(P @ r.x + q + A.T @ r.y))
+    eps_pri = 1e-5 + 1e-5 * max(np.max(np.abs(Ax)), np.max(np.abs(z)))
+    eps_dua = 1e-5 + 1e-5 * max(np.max(np.abs(P @ r.x)), np.max(np.abs(A.T @ r.y)), np.max(np.abs(q)))
+    assert pri <= 2 * eps_pri and dua <= 2 * eps_dua
+    # complementary slackness in sign form: y+ only where the upper bound is (nearly) active, y- lower
+    tol = 1e-3
+    assert np.all((r.y <= tol) | (u - Ax <= 1e-2))
+    assert np.all((r.y >= -tol) | (Ax - l <= 1e-2))
+    assert abs(r.info.obj_val - (0.5 * r.x @ (P @ r.x) + q @ r.x)) <= 1e-6 * (1 + abs(r.info.obj_val))
