@@ -36,9 +36,11 @@ typedef struct {
 /* Measurement of the last osqp_solve on this workspace. */
 c_int osqp_b200_get_profile(const OSQPWorkspace *work, OSQPB200Profile *out);
 
-/* Inner-solver controls: ||r||inf <= max(rel_tol*||b||inf, abs_tol); values <= 0 keep the current one.
- * refresh_every: rebuild z~ = A x~ and r = b - K x~ from scratch every k ADMM iterations (0: only when needed). */
-c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float rel_tol, c_float abs_tol, c_int max_iter, c_int refresh_every);
+/* Inner-solver controls.  Each ADMM step's PCG stops at ||r||inf <= max(eta*||r0||inf, floor_rel*||b||inf)
+ * where r0 is the residual the step starts from (defaults 1e-3, 1e-13; DESIGN.md "inner accuracy").
+ * Values <= 0 keep the current one.  refresh_every: rebuild z~ = A x~ and r = b - K x~ from scratch
+ * every k ADMM iterations (0: only when K or the iterates were changed from outside). */
+c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float eta, c_float floor_rel, c_int max_iter, c_int refresh_every);
 
 /* Standalone SpMV with the resident (scaled) matrices, same device code and work split as the ADMM
  * kernel.  which: 0 out=A in | 1 out=A' in | 2 out=(P+sigma I) in.  Host buffers; runs `reps`

@@ -53,7 +53,7 @@ constexpr int kPrintInterval = 200;
 const double kNaN = std::numeric_limits<double>::quiet_NaN();
 
 // process-global backend selection (see osqp_oracle_configure)
-int g_linsys_mode = 0;  // 0 direct, 1 pcg
+int g_linsys_mode = 0;  // 0 direct, 1 pcg (residual criterion), 2 pcg (preconditioned-residual criterion), 3 pcg (relative-to-initial-residual criterion)
 double g_pcg_tol = 1e-9;
 idx_t g_pcg_max_iter = 0;  // 0 => 10 * n, capped
 
@@ -277,6 +277,7 @@ struct DirectLdl : LinSys {
 struct ReducedPcg : LinSys {
   idx_t n, m;
   double sigma, tol;
+  bool precond_norm = false, rel_init = false;
   idx_t max_it;
   vec rho;
   // CSR of A, CSR of A' (= CSC of A), full symmetric P in CSR
@@ -287,6 +288,8 @@ struct ReducedPcg : LinSys {
   int init(const Csc &P, const Csc &A, double sigma_, const vec &rho_vec) {
     n = P.n; m = A.m; sigma = sigma_; rho = rho_vec;
     tol = g_pcg_tol;
+    precond_norm = (g_linsys_mode == 2);
+    rel_init = (g_linsys_mode == 3);
     max_it = g_pcg_max_iter > 0 ? g_pcg_max_iter : std::max<idx_t>(20, std::min<idx_t>(10 * n, 5000));
     xk.assign(n, 0.0); r.resize(n); d.resize(n); p.resize(n); Kp_.resize(n); t.resize(m); rhs.resize(n);
     return update_matrices(P, A);
@@ -361,24 +364,30 @@ struct ReducedPcg : LinSys {
   int solve(double *b) override {
     stat_b += 1;
     // rhs = b_x + A'(rho .* b_z)
+#pragma omp parallel for schedule(static)
     for (idx_t i = 0; i < m; i++) t[i] = rho[i] * b[n + i];
+#pragma omp parallel for schedule(static)
     for (idx_t j = 0; j < n; j++) {
       double s = b[j];
       for (idx_t k = Tp[j]; k < Tp[j + 1]; k++) s += Tx[k] * t[Tj[k]];
       rhs[j] = s;
     }
-    double bnorm = norm_inf(rhs);
+    double bnorm = 0;
+    if (precond_norm) for (idx_t j = 0; j < n; j++) bnorm = std::max(bnorm, std::fabs(Minv[j] * rhs[j]));
+    else bnorm = norm_inf(rhs);
     double thresh = std::max(tol * bnorm, 1e-300);
     apply_K(xk.data(), Kp_.data());
     double rz = 0, rn = 0;
+#pragma omp parallel for reduction(+ : rz) reduction(max : rn) schedule(static)
     for (idx_t j = 0; j < n; j++) {
       r[j] = rhs[j] - Kp_[j];
       d[j] = Minv[j] * r[j];
       p[j] = d[j];
       rz += r[j] * d[j];
-      rn = std::max(rn, std::fabs(r[j]));
+      rn = std::max(rn, std::fabs(precond_norm ? d[j] : r[j]));
     }
     idx_t it = 0;
+    if (rel_init) thresh = std::max(tol * rn, 1e-13 * bnorm);
     while (rn > thresh && it < max_it) {
       apply_K(p.data(), Kp_.data());
       double pKp = 0;
@@ -393,7 +402,7 @@ struct ReducedPcg : LinSys {
         r[j] -= a * Kp_[j];
         d[j] = Minv[j] * r[j];
         rz_new += r[j] * d[j];
-        rn = std::max(rn, std::fabs(r[j]));
+        rn = std::max(rn, std::fabs(precond_norm ? d[j] : r[j]));
       }
       double beta = rz_new / rz;
       rz = rz_new;
@@ -955,7 +964,7 @@ void begin_update(Work &w) {
 }
 
 int make_linsys(Work &w) {
-  if (w.linsys_mode == 1) {
+  if (w.linsys_mode >= 1) {
     auto s = std::make_unique<ReducedPcg>();
     int e = s->init(w.P, w.A, w.st.sigma, w.rho_vec);
     w.lin = std::move(s);
@@ -1235,7 +1244,7 @@ static c_int update_PA(Work &w, const c_float *Px_new, const c_int *Px_idx, c_in
   if (w.st.scaling) scale_data(w);
   // NB libosqp keeps rho_vec as is here (constraint types are re-derived only on bound updates)
   int e = w.lin->update_matrices(w.P, w.A);
-  if (w.linsys_mode == 1) w.lin->update_rho_vec(w.rho_vec);
+  if (w.linsys_mode >= 1) w.lin->update_rho_vec(w.rho_vec);
   reset_info(w.info);
   if (e < 0) fprintf(stderr, "ERROR in osqp_update_P/A: new KKT matrix is not quasidefinite\n");
   w.info.update_time += now_s() - t0;

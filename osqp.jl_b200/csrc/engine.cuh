@@ -105,7 +105,8 @@ struct SolveCfg {
   int verbose;
   double time_limit_s;     // <= 0: none; budget left for this solve (base time already subtracted)
   // PCG controls (engine-specific; include/osqp_b200.h)
-  double pcg_rel_tol, pcg_abs_tol;
+  double pcg_eta;          // PCG stops at |r|inf <= max(pcg_eta * |r0|inf, pcg_floor * |b|inf)
+  double pcg_floor;
   int pcg_max_iter;
   int refresh_every;       // recompute z_tilde = A x_tilde and r = b - K x_tilde every k ADMM iterations (1 = always)
 };

@@ -532,7 +532,9 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
     refreshes += refresh;
     refresh = 0;
     {
-      const double thresh = fmax(c.pcg_rel_tol * red3[2], c.pcg_abs_tol);
+      // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
+      // (r0 measures how far the system moved since the last solve), floored at roundoff level
+      const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
       const int ncg = pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1], thresh,
                               c.pcg_max_iter, m0, m1, n0, n1);
       cg_total += ncg;

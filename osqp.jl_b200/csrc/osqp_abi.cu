@@ -65,7 +65,7 @@ struct Engine {
   long long *stage_idx = nullptr;
   long long stage_cap = 0;
   // engine controls
-  double pcg_rel_tol = 0.0 /* 0 = auto: min(1e-7, 0.01*max(eps_abs, eps_rel)) */, pcg_abs_tol = 1e-14;
+  double pcg_eta = 1e-3, pcg_floor = 1e-13;
   int pcg_max_iter = 0, refresh_every = 25;
   double polish_penalty = 1e4;
   bool first_run = true, clear_update_time = false;
@@ -368,8 +368,8 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   CU_OK(cudaEventCreate(&e.ev1));
   CU_OK(cudaEventCreate(&e.ev2));
   e.st = *settings;
-  e.pcg_rel_tol = env_double("OSQP_B200_PCG_TOL", e.pcg_rel_tol);
-  e.pcg_abs_tol = env_double("OSQP_B200_PCG_ABS_TOL", e.pcg_abs_tol);
+  e.pcg_eta = env_double("OSQP_B200_PCG_ETA", e.pcg_eta);
+  e.pcg_floor = env_double("OSQP_B200_PCG_FLOOR", e.pcg_floor);
   e.refresh_every = env_int("OSQP_B200_REFRESH_EVERY", e.refresh_every);
   e.polish_penalty = env_double("OSQP_B200_POLISH_PENALTY", e.polish_penalty);
   const int n = (int)data->n, m = (int)data->m;
@@ -563,11 +563,7 @@ c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
   c.warm_start = (int)e.st.warm_start; c.verbose = (int)e.st.verbose;
   const double base = e.first_run ? e.info.setup_time : e.info.update_time;
   c.time_limit_s = e.st.time_limit > 0 ? e.st.time_limit - base : -1e30;
-  // Inner accuracy follows the outer tolerance: the oracle study in DESIGN.md shows the ADMM iterates
-  // track the exact-solve trajectory (same iteration count, errors << eps) at 1e-2 * eps.
-  c.pcg_rel_tol = e.pcg_rel_tol > 0 ? e.pcg_rel_tol
-                                    : std::max(1e-13, std::min(1e-7, 0.01 * std::max(e.st.eps_abs, e.st.eps_rel)));
-  c.pcg_abs_tol = e.pcg_abs_tol; c.pcg_max_iter = e.pcg_max_iter;
+  c.pcg_eta = e.pcg_eta; c.pcg_floor = e.pcg_floor; c.pcg_max_iter = e.pcg_max_iter;
   c.refresh_every = e.refresh_every;
   if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
 
@@ -923,11 +919,11 @@ c_int osqp_b200_get_profile(const OSQPWorkspace *work, OSQPB200Profile *out) {
   return 0;
 }
 
-c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float rel_tol, c_float abs_tol, c_int max_iter, c_int refresh_every) {
+c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float eta, c_float floor_rel, c_int max_iter, c_int refresh_every) {
   if (!work) return 1;
   Engine &e = *E(work);
-  if (rel_tol > 0) e.pcg_rel_tol = rel_tol;
-  if (abs_tol > 0) e.pcg_abs_tol = abs_tol;
+  if (eta > 0) e.pcg_eta = eta;
+  if (floor_rel > 0) e.pcg_floor = floor_rel;
   if (max_iter > 0) e.pcg_max_iter = (int)max_iter;
   if (refresh_every >= 0) e.refresh_every = (int)refresh_every;
   return 0;
