@@ -43,13 +43,17 @@ c_int osqp_b200_get_profile(const OSQPWorkspace *work, OSQPB200Profile *out);
 c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float eta, c_float floor_rel, c_int max_iter, c_int refresh_every);
 
 /* Standalone SpMV with the resident (scaled) matrices, same device code and work split as the ADMM
- * kernel.  which: 0 out=A in | 1 out=A' in | 2 out=(P+sigma I) in.  Host buffers; runs `reps`
- * launches and returns the mean CUDA-event time per launch in *ms_per_rep. */
+ * kernel.  which: 0 out=A in | 1 out=A' in | 2 out=(P+sigma I) in on the hot-path format (column-blocked,
+ * vector tile staged in shared memory by TMA); 10/11/12: same products on the CSR + L1-gather path used by
+ * the rare phases.  Host buffers; runs `reps` launches, returns the mean CUDA-event time per launch. */
 c_int osqp_b200_spmv(OSQPWorkspace *work, c_int which, const c_float *in_host, c_float *out_host, c_int reps,
                      c_float *ms_per_rep);
 
 /* Scaling computed at setup: D (n), E (m), c -- for parity checks against the oracle. */
 c_int osqp_b200_get_scaling(OSQPWorkspace *work, c_float *D, c_float *E, c_float *c);
+
+/* Debug: per-block globaltimer probes written by the last blocked osqp_b200_spmv launch ([grid][16]). */
+c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int count);
 
 c_int osqp_b200_device_count(void);
 

@@ -28,6 +28,21 @@ struct CsrDev {
   int lanes = 32;          // lanes cooperating on one row (power of two <= 32)
 };
 
+// Column-blocked copy of a CSR matrix for the hot SpMV phases: the dense input vector is staged
+// one block of W columns at a time in shared memory (TMA bulk copy) and gathered from there, so
+// column indices are block-local 16-bit values (10 B / nnz instead of 12) and no random 8-byte
+// gather ever reaches L2.  Block cb holds, row by row, the entries with cb*W <= col < (cb+1)*W.
+struct BlkDev {
+  int nb = 0;                    // number of column blocks
+  int W = 0;                     // columns per block (multiple of 32, W*8 bytes fit in shared memory)
+  int rows = 0, cols = 0;
+  int lanes = 8;                 // threads cooperating on one row segment
+  int *rowptr = nullptr;         // [nb][rows+1] absolute positions into col/val (block-major storage)
+  unsigned short *col = nullptr; // column index local to the block
+  double *val = nullptr;         // scaled values
+  int *from_csr = nullptr;       // CSR position -> blocked position (value refresh after re-scaling)
+};
+
 // Persistent solver state that survives between launches (device memory).
 struct DevState {
   double rho;              // current scalar rho (settings->rho)
@@ -82,6 +97,15 @@ struct DevPtrs {
   double *pol_y = nullptr, *pol_z = nullptr, *pol_rho = nullptr, *pol_b = nullptr;  // m
   // results
   double *sol_x = nullptr, *sol_y = nullptr;
+  // column-blocked copies for the hot phases (blocked == 0: fall back to the CSR + L1 gather path)
+  int blocked = 0;
+  BlkDev Ab, Pb, Atb;
+  double *Pu = nullptr;          // n: P u of the current PCG iteration
+  double *partAt = nullptr;      // [Atb.nb][n] partial sums of A' w per column block
+  int at_ntiles = 0;             // A' tiles (column block x row range), tile t is processed by block t % grid
+  int *at_tile_cb = nullptr, *at_tile_r0 = nullptr, *at_tile_r1 = nullptr;
+  int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged vector tile
+  int smem_rows = 0;             // doubles of dynamic shared memory for per-row running sums
   // work partition: block b owns rows [m_start[b], m_start[b+1]) of A and [n_start[b], n_start[b+1]) of P/A'
   int *m_start = nullptr, *n_start = nullptr;
   // grid barrier + reductions
@@ -89,6 +113,7 @@ struct DevPtrs {
   double *red = nullptr;    // [2][kRedSlots][grid]
   DevState *state = nullptr;
   DevInfo *info = nullptr;
+  unsigned long long *dbg = nullptr;  // [grid][16] globaltimer probes (spmv_blk_kernel only)
 };
 
 struct SolveCfg {
@@ -129,6 +154,7 @@ struct PolishOut {
 
 struct LaunchGeom {
   int grid = 1, block = 1024;
+  size_t dyn_smem = 0;
 };
 
 // ---- host wrappers implemented in kernels.cu (all asynchronous on `st`)
@@ -147,6 +173,8 @@ cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg
                           cudaStream_t st);
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
                         cudaStream_t st);
-int max_coop_blocks_per_sm(int block);
+int max_coop_blocks_per_sm(int block, size_t dyn_smem);
+cudaError_t configure_dyn_smem(size_t dyn_smem);
+cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
 
 }  // namespace osqpb200

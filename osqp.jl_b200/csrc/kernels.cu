@@ -52,6 +52,148 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+__device__ __forceinline__ unsigned ld_stream(const unsigned short *p) {
+  unsigned short v;
+  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+  return v;
+}
+
+// ------------------------------------------------------------------ shared-memory staging of the dense vector tile (TMA)
+// One elected thread arms an mbarrier with the byte count and issues 1-D bulk async copies
+// (cp.async.bulk.shared.global -> UBLKCP); every thread then waits on the mbarrier phase.
+struct Stage {
+  double *xs;                  // staged tile of the gathered vector
+  double *rowsum;              // running row sums across column blocks (row-owner phases)
+  unsigned long long *mbar;
+  unsigned parity;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void stage_init(Stage &S, const DevPtrs &d) {
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  S.xs = reinterpret_cast<double *>(dyn_smem);
+  S.rowsum = S.xs + d.smem_x_elems;
+  S.mbar = reinterpret_cast<unsigned long long *>(S.rowsum + d.smem_rows);
+  S.parity = 0;
+  if (d.blocked) {
+    if (threadIdx.x == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S.mbar)));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
+}
+
+// Copy `count` doubles from global `src` (16 B aligned, readable up to the next even count) into S.xs.
+// Caller guarantees every thread has finished reading the previous tile (a __syncthreads()).
+__device__ __forceinline__ void stage_tile(Stage &S, const double *src, int count) {
+  const unsigned bytes = ((unsigned)count * 8u + 15u) & ~15u;
+  const unsigned mbar = smem_u32(S.mbar);
+  if (threadIdx.x == 0) {
+    // the tile was written with ordinary stores by other blocks before the grid barrier:
+    // order those generic-proxy writes before the async-proxy (TMA) reads
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    const unsigned dst = smem_u32(S.xs);
+    const char *g = reinterpret_cast<const char *>(src);
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+      const unsigned chunk = (bytes - off < 32768u) ? (bytes - off) : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       dst + off),
+                   "l"(g + off), "r"(chunk), "r"(mbar)
+                   : "memory");
+    }
+  }
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(mbar), "r"(S.parity)
+        : "memory");
+  }
+  S.parity ^= 1u;
+}
+
+// rows [r0, r1) of column block cb against the staged tile xs; epilogue(row, partial sum) on lane 0 of the group.
+// Software pipelined: a group of `lanes` threads owns rows r0+grp, r0+grp+ngrp, ... and keeps TWO rows'
+// (value, column) loads in flight in registers (kSlots strided elements each) while it reduces the row
+// before them; the row pointers are fetched two rows ahead.  With 1024 threads that is ~80 KB of matrix
+// stream in flight per SM at all times, which is what a ~1 us HBM round trip needs at 44 GB/s per SM;
+// the gather itself hits shared memory.  Rows longer than lanes*kSlots fall into a (non-pipelined) tail loop.
+constexpr int kSlots = 4;
+
+template <typename Epi>
+__device__ __forceinline__ void blk_rows(const BlkDev &B, int cb, int r0, int r1, const double *xs, Epi epi) {
+  const int lanes = B.lanes;
+  const int tid = threadIdx.x, sub = tid & (lanes - 1), grp = tid / lanes, ngrp = blockDim.x / lanes;
+  const int *rp = B.rowptr + (size_t)cb * (B.rows + 1);
+  const double *__restrict__ val = B.val;
+  const unsigned short *__restrict__ col = B.col;
+
+  auto load_rp = [&](int row, int &k0, int &k1) {
+    const bool valid = row < r1;
+    k0 = valid ? ld_stream(rp + row) : 0;
+    k1 = valid ? ld_stream(rp + row + 1) : 0;
+  };
+  auto issue = [&](int k0, int k1, double (&v)[kSlots], unsigned (&c)[kSlots]) {
+#pragma unroll
+    for (int t = 0; t < kSlots; t++) {
+      const int kk = k0 + sub + t * lanes;
+      const bool in = kk < k1;
+      v[t] = in ? ld_stream(val + kk) : 0.0;
+      c[t] = in ? ld_stream(col + kk) : 0u;
+    }
+  };
+  auto consume = [&](int row, int k0, int k1, double (&v)[kSlots], unsigned (&c)[kSlots]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int t = 0; t < kSlots; t++)
+      if (k0 + sub + t * lanes < k1) acc += v[t] * xs[c[t]];
+    for (int kk = k0 + sub + kSlots * lanes; kk < k1; kk += lanes) acc += ld_stream(val + kk) * xs[ld_stream(col + kk)];
+    __syncwarp();
+    for (int o = lanes >> 1; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, lanes);
+    if (sub == 0 && row < r1) epi(row, acc);
+  };
+
+  int rowA = r0 + grp, rowB = rowA + ngrp;
+  int a0, a1, b0, b1;
+  load_rp(rowA, a0, a1);
+  load_rp(rowB, b0, b1);
+  double vA[kSlots], vB[kSlots];
+  unsigned cA[kSlots], cB[kSlots];
+  issue(a0, a1, vA, cA);
+  for (int base = r0; base < r1; base += 2 * ngrp) {  // trip count uniform over the block
+    issue(b0, b1, vB, cB);
+    int n0, n1;
+    load_rp(rowA + 2 * ngrp, n0, n1);
+    consume(rowA, a0, a1, vA, cA);
+    rowA += 2 * ngrp; a0 = n0; a1 = n1;
+    issue(a0, a1, vA, cA);
+    load_rp(rowB + 2 * ngrp, n0, n1);
+    consume(rowB, b0, b1, vB, cB);
+    rowB += 2 * ngrp; b0 = n0; b1 = n1;
+  }
+}
+
+// A' tiles (column block x row range) against `vec` (m): partial sums into d.partAt[cb][row]; dot(row, partial) on lane 0
+template <typename Dot>
+__device__ __forceinline__ void at_tiles(Stage &S, const DevPtrs &d, const double *vec, Dot dot) {
+  for (int t = blockIdx.x; t < d.at_ntiles; t += gridDim.x) {
+    const int cb = d.at_tile_cb[t], r0 = d.at_tile_r0[t], r1 = d.at_tile_r1[t];
+    const int c0 = cb * d.Atb.W;
+    const int cnt = (d.m - c0 < d.Atb.W) ? (d.m - c0) : d.Atb.W;
+    __syncthreads();
+    stage_tile(S, vec + c0, cnt);
+    double *out = d.partAt + (size_t)cb * d.n;
+    blk_rows(d.Atb, cb, r0, r1, S.xs, [&](int row, double acc) {
+      out[row] = acc;
+      dot(row, acc);
+    });
+  }
+}
+
 // ------------------------------------------------------------------ grid barrier + reductions
 struct Grid {
   unsigned *count, *gen;
@@ -292,6 +434,101 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, const DevPtrs &d, cons
   return it;
 }
 
+// Same recurrence on the column-blocked matrices with the gathered vector staged in shared memory:
+//   phase A': every block walks the column blocks of the n-dimension (stage uu[cb] once, use it for
+//             its rows of A *and* of P; running row sums in shared memory) -> t, tr = rho.*t, Pu
+//   phase B': one A' tile (column block x row range) per block, tr[cb] staged -> partAt[cb][:]
+//   phase V : w = Pu + sigma uu + sum_cb partAt[cb]; delta was already accumulated tile by tile
+__device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const DevPtrs &d, const PcgVecs &v,
+                                        const double *rho_vec, const double *Minv, double sigma, double *xvec,
+                                        double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
+                                        int m1, int n0, int n1) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int nbN = d.Pb.nb, nbM = (d.m > 0) ? d.Atb.nb : 0, n = d.n;
+  const int mrows = m1 - m0;
+  double a_old = 1.0, gamma_old = 1.0;
+  int it = 0;
+  while (rn > thresh && it < max_it) {
+    double red1[1] = {0.0};
+    // ---- phase A'
+    for (int cb = 0; cb < nbN; cb++) {
+      const int c0 = cb * d.Pb.W;
+      const int cnt = (n - c0 < d.Pb.W) ? (n - c0) : d.Pb.W;
+      __syncthreads();
+      stage_tile(S, v.uu + c0, cnt);
+      const bool first = (cb == 0), last = (cb == nbN - 1);
+      if (d.m > 0)
+        blk_rows(d.Ab, cb, m0, m1, S.xs, [&](int row, double acc) {
+          const double sres = first ? acc : S.rowsum[row - m0] + acc;
+          if (last) {
+            v.t[row] = sres;
+            v.tr[row] = rho_vec[row] * sres;
+          } else {
+            S.rowsum[row - m0] = sres;
+          }
+        });
+      blk_rows(d.Pb, cb, n0, n1, S.xs, [&](int row, double acc) {
+        const double sres = first ? acc : S.rowsum[mrows + row - n0] + acc;
+        if (last) {
+          const double uj = v.uu[row];
+          d.Pu[row] = sres;
+          red1[0] += uj * (sres + sigma * uj);
+        } else {
+          S.rowsum[mrows + row - n0] = sres;
+        }
+      });
+    }
+    if (d.m > 0) {
+      grid_barrier(g);
+      // ---- phase B'
+      at_tiles(S, d, v.tr, [&](int row, double acc) { red1[0] += v.uu[row] * acc; });
+    }
+    reduce_and_barrier<1>(g, sm, red1, 0u);
+    const double delta = red1[0];
+    double beta, alpha;
+    if (it == 0) {
+      beta = 0.0;
+      alpha = gamma / delta;
+    } else {
+      beta = gamma / gamma_old;
+      alpha = gamma / (delta - beta * gamma / a_old);
+    }
+    if (!(alpha > 0.0) || !isfinite(alpha)) break;
+    // ---- phase V
+    double red2[2] = {0.0, 0.0};
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double uj = v.uu[j];
+      double wj = d.Pu[j] + sigma * uj;
+      for (int cb = 0; cb < nbM; cb++) wj += d.partAt[(size_t)cb * n + j];
+      const double pj = (it == 0) ? uj : uj + beta * v.p[j];
+      const double sj = (it == 0) ? wj : wj + beta * v.s[j];
+      v.p[j] = pj;
+      v.s[j] = sj;
+      xvec[j] += alpha * pj;
+      const double rj = v.r[j] - alpha * sj;
+      v.r[j] = rj;
+      const double un = Minv[j] * rj;
+      v.uu[j] = un;
+      red2[0] += rj * un;
+      red2[1] = fmax(red2[1], fabs(rj));
+    }
+    if (zvec != nullptr) {
+      for (int i = m0 + tid; i < m1; i += nth) {
+        const double api = (it == 0) ? v.t[i] : v.t[i] + beta * v.Ap[i];
+        v.Ap[i] = api;
+        zvec[i] += alpha * api;
+      }
+    }
+    reduce_and_barrier<2>(g, sm, red2, 0x2u);
+    gamma_old = gamma;
+    gamma = red2[0];
+    rn = red2[1];
+    a_old = alpha;
+    it++;
+  }
+  return it;
+}
+
 // ------------------------------------------------------------------ update_info (row a9) + infeasibility products (row a10)
 // One phase streams A, P and A' once each with two gathered vectors per matrix:
 //   A:(x, dx) -> Ax, A dx | P:(x, dx) -> Px, P dx | A':(y, dy) -> A'y, A'dy
@@ -448,6 +685,8 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
+  Stage SG;
+  stage_init(SG, d);
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
   const int lanesA = d.A.lanes, lanesN = d.At.lanes;
@@ -495,6 +734,27 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
     grid_barrier(g);
     // ---- P2: b = sigma x - q + A' wv ; r = b - K x_tilde (refresh) or r += b - b_old
     double red3[3] = {0.0, 0.0, 0.0};
+    if (d.blocked && !refresh) {
+      // steady state: A' wv through the staged tiles, then the element-wise part on the owner block
+      if (d.m > 0) {
+        at_tiles(SG, d, d.wv, [](int, double) {});
+        grid_barrier(g);
+      }
+      const int nbM = (d.m > 0) ? d.Atb.nb : 0;
+      for (int j = n0 + tid; j < n1; j += nth) {
+        double acc = 0.0;
+        for (int cb = 0; cb < nbM; cb++) acc += d.partAt[(size_t)cb * d.n + j];
+        const double bj = c.sigma * d.x[j] - d.q[j] + acc;
+        const double rj = d.r[j] + (bj - d.b[j]);
+        d.b[j] = bj;
+        d.r[j] = rj;
+        const double uj = d.Minv[j] * rj;
+        d.uu[j] = uj;
+        red3[0] += rj * uj;
+        red3[1] = fmax(red3[1], fabs(rj));
+        red3[2] = fmax(red3[2], fabs(bj));
+      }
+    } else
     for (int base = n0; base < n1; base += ngrpN) {
       const int row = base + grpN;
       const bool valid = row < n1;
@@ -535,8 +795,10 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
       // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
       // (r0 measures how far the system moved since the last solve), floored at roundoff level
       const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
-      const int ncg = pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1], thresh,
-                              c.pcg_max_iter, m0, m1, n0, n1);
+      const int ncg = d.blocked ? pcg_run_blk(g, sm, SG, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                                              red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+                                : pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
+                                          thresh, c.pcg_max_iter, m0, m1, n0, n1);
       cg_total += ncg;
       cg_solves++;
     }
@@ -768,6 +1030,8 @@ __global__ void __launch_bounds__(1024, 1) polish_kernel(const DevPtrs d, const 
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
+  Stage SG;
+  stage_init(SG, d);
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
   const int lanesA = d.A.lanes, lanesN = d.At.lanes;
@@ -840,8 +1104,10 @@ __global__ void __launch_bounds__(1024, 1) polish_kernel(const DevPtrs d, const 
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
-    cg_total += pcg_run(g, sm, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1], thresh,
-                        c.pcg_max_iter, m0, m1, n0, n1);
+    cg_total += d.blocked ? pcg_run_blk(g, sm, SG, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
+                                        red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+                          : pcg_run(g, sm, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1],
+                                    thresh, c.pcg_max_iter, m0, m1, n0, n1);
     // multiplier step on active rows: y += penalty (A x - b)
     for (int i = m0 + tid; i < m1; i += nth)
       if (d.pol_rho[i] > 0.0) d.pol_y[i] += d.pol_rho[i] * (d.pol_z[i] - d.pol_b[i]);
@@ -934,6 +1200,48 @@ __global__ void __launch_bounds__(1024, 1) spmv_kernel(const DevPtrs d, int whic
       group_reduce<1>(acc, lanesN);
       if (valid && subN == 0) out[row] = acc.a[0] + (which == 2 ? sigma * in[row] : 0.0);
     }
+  }
+}
+
+// Standalone SpMV on the column-blocked copies: exactly the phase code of pcg_run_blk (A / P: row owner over
+// the column blocks; A': tiles -> partials -> owner sum after one grid barrier).
+__global__ void __launch_bounds__(1024, 1) spmv_blk_kernel(const DevPtrs d, int which, const double *in, double *out,
+                                                            double sigma) {
+  Grid g;
+  grid_init(g, d);
+  Stage SG;
+  stage_init(SG, d);
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
+  const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
+  if (which == 1) {
+    at_tiles(SG, d, in, [](int, double) {});
+    grid_barrier(g);
+    for (int j = n0 + tid; j < n1; j += nth) {
+      double acc = 0.0;
+      for (int cb = 0; cb < d.Atb.nb; cb++) acc += d.partAt[(size_t)cb * d.n + j];
+      out[j] = acc;
+    }
+    return;
+  }
+  const BlkDev &B = (which == 0) ? d.Ab : d.Pb;
+  const int r0 = (which == 0) ? m0 : n0, r1 = (which == 0) ? m1 : n1;
+  unsigned long long *probe = d.dbg + (size_t)b * 16;
+  int np = 0;
+  if (tid == 0) probe[np++] = globaltimer_ns();
+  for (int cb = 0; cb < B.nb; cb++) {
+    const int c0 = cb * B.W;
+    const int cnt = (d.n - c0 < B.W) ? (d.n - c0) : B.W;
+    __syncthreads();
+    stage_tile(SG, in + c0, cnt);
+    if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
+    const bool first = (cb == 0), last = (cb == B.nb - 1);
+    blk_rows(B, cb, r0, r1, SG.xs, [&](int row, double acc) {
+      const double sres = first ? acc : SG.rowsum[row - r0] + acc;
+      if (last) out[row] = sres + (which == 2 ? sigma * in[row] : 0.0);
+      else SG.rowsum[row - r0] = sres;
+    });
+    __syncthreads();
+    if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
   }
 }
 
@@ -1149,6 +1457,16 @@ __global__ void k_scatter(double *dst, const double *vals, const long long *idx,
   }
 }
 
+// blocked copies <- scaled CSR values
+__global__ void k_fill_blocked(const DevPtrs d) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  for (long long k = tid; k < d.A.nnz; k += nth) {
+    d.Ab.val[d.Ab.from_csr[k]] = d.A.val[k];
+    d.Atb.val[d.Atb.from_csr[k]] = d.At.val[k];
+  }
+  for (long long k = tid; k < d.P.nnz; k += nth) d.Pb.val[d.Pb.from_csr[k]] = d.P.val[k];
+}
+
 inline int ew_grid(long long work) {
   long long g = (work + 255) / 256;
   if (g < 1) g = 1;
@@ -1159,7 +1477,7 @@ inline int ew_grid(long long work) {
 template <typename... Args>
 cudaError_t coop_launch(void (*kernel)(Args...), LaunchGeom g, cudaStream_t st, Args... args) {
   void *params[] = {(void *)&args...};
-  return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, 0, st);
+  return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, g.dyn_smem, st);
 }
 
 }  // namespace
@@ -1201,6 +1519,7 @@ cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st) {
 }
 
 cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st) {
+  g.dyn_smem = 0;
   return coop_launch(pd_probe_kernel, g, st, d, sigma, max_it);
 }
 
@@ -1227,16 +1546,32 @@ cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cu
 
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
                         cudaStream_t st) {
-  spmv_kernel<<<g.grid, g.block, 0, st>>>(d, which, in, out, sigma);
-  return cudaGetLastError();
+  if (which >= 10 || !d.blocked) {  // CSR + L1-gather path
+    spmv_kernel<<<g.grid, g.block, 0, st>>>(d, which % 10, in, out, sigma);
+    return cudaGetLastError();
+  }
+  return coop_launch(spmv_blk_kernel, g, st, d, which, in, out, sigma);
 }
 
-int max_coop_blocks_per_sm(int block) {
+cudaError_t configure_dyn_smem(size_t dyn_smem) {
+  cudaError_t e = cudaFuncSetAttribute(admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(spmv_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+}
+
+int max_coop_blocks_per_sm(int block, size_t dyn_smem) {
   int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, admm_kernel, block, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, admm_kernel, block, dyn_smem) != cudaSuccess) return 0;
   int nb2 = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, polish_kernel, block, 0) != cudaSuccess) return 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, polish_kernel, block, dyn_smem) != cudaSuccess) return 0;
   return nb < nb2 ? nb : nb2;
+}
+
+cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st) {
+  if (d.blocked) k_fill_blocked<<<ew_grid(d.A.nnz + d.P.nnz), 256, 0, st>>>(d);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,

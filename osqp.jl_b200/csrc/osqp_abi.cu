@@ -225,14 +225,73 @@ void balanced_split(const std::vector<long long> &w_prefix, int rows, int parts,
   start[parts] = rows;
 }
 
+// Column-blocked copy of a host CSR matrix (engine.cuh BlkDev): block-major storage, 16-bit local columns.
+struct BlkHost {
+  int nb = 0, W = 0;
+  std::vector<int> rowptr, from_csr;
+  std::vector<unsigned short> col;
+};
+void build_blocked(const std::vector<int> &rowptr, const std::vector<int> &col, int rows, int cols, int W,
+                   BlkHost &out) {
+  const int nb = std::max(1, (cols + W - 1) / W);
+  out.nb = nb;
+  out.W = W;
+  const long long nnz = rowptr[rows];
+  out.rowptr.assign((size_t)nb * (rows + 1), 0);
+  out.from_csr.resize(nnz);
+  out.col.resize(nnz);
+  // count per (block, row)
+  for (int r = 0; r < rows; r++)
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) out.rowptr[(size_t)(col[k] / W) * (rows + 1) + r + 1]++;
+  long long run = 0;
+  for (int cb = 0; cb < nb; cb++) {
+    int *rp = out.rowptr.data() + (size_t)cb * (rows + 1);
+    rp[0] = (int)run;
+    for (int r = 0; r < rows; r++) {
+      const int cnt = rp[r + 1];
+      rp[r + 1] = rp[r] + cnt;
+    }
+    run = rp[rows];
+  }
+  std::vector<int> fill((size_t)nb * rows);
+  for (int cb = 0; cb < nb; cb++)
+    for (int r = 0; r < rows; r++) fill[(size_t)cb * rows + r] = out.rowptr[(size_t)cb * (rows + 1) + r];
+  for (int r = 0; r < rows; r++)
+    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
+      const int cb = col[k] / W;
+      const int pos = fill[(size_t)cb * rows + r]++;
+      out.from_csr[k] = pos;
+      out.col[pos] = (unsigned short)(col[k] - cb * W);
+    }
+}
+
+c_int upload_blk(Engine &e, const BlkHost &h, int rows, int cols, BlkDev &b) {
+  const long long nnz = (long long)h.col.size();
+  b.nb = h.nb; b.W = h.W; b.rows = rows; b.cols = cols;
+  const double avg = (double)nnz / std::max(1.0, (double)rows * h.nb);
+  int l = 1;
+  while (l < 32 && (double)l * 4.0 < avg) l <<= 1;
+  b.lanes = env_int("OSQP_B200_BLK_LANES", l);
+  CU_OK(dalloc(e, &b.rowptr, h.rowptr.size()));
+  CU_OK(dalloc(e, &b.col, (size_t)nnz + 8));
+  CU_OK(dalloc(e, &b.val, (size_t)nnz + 8));
+  CU_OK(dalloc(e, &b.from_csr, (size_t)nnz));
+  CU_OK(cudaMemcpyAsync(b.rowptr, h.rowptr.data(), h.rowptr.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  if (nnz > 0) {
+    CU_OK(cudaMemcpyAsync(b.col, h.col.data(), nnz * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
+    CU_OK(cudaMemcpyAsync(b.from_csr, h.from_csr.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  }
+  CU_OK(cudaStreamSynchronize(e.stream));
+  return 0;
+}
+
 c_int upload_partition(Engine &e, const std::vector<int> &A_rowptr, const std::vector<int> &At_rowptr,
-                       const std::vector<int> &P_rowptr) {
+                       const std::vector<int> &P_rowptr, std::vector<int> &ms, std::vector<int> &ns) {
   const int n = e.d.n, m = e.d.m, grid = e.geom.grid;
   std::vector<long long> wm(m + 1, 0), wn(n + 1, 0);
   for (int i = 0; i < m; i++) wm[i + 1] = wm[i] + (A_rowptr[i + 1] - A_rowptr[i]) + 4;
   for (int j = 0; j < n; j++)
     wn[j + 1] = wn[j] + (P_rowptr[j + 1] - P_rowptr[j]) + (m > 0 ? At_rowptr[j + 1] - At_rowptr[j] : 0) + 4;
-  std::vector<int> ms, ns;
   balanced_split(wm, m, grid, ms);
   balanced_split(wn, n, grid, ns);
   CU_OK(cudaMemcpyAsync(e.d.m_start, ms.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice, e.stream));
@@ -260,7 +319,8 @@ c_int rescale_and_refresh(Engine &e, bool reset_rho_types) {
     e.prof.launches += 1;
   }
   CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
-  e.prof.launches += 1;
+  CU_OK(launch_fill_blocked(e.d, e.stream));
+  e.prof.launches += 2;
   return 0;
 }
 
@@ -328,6 +388,15 @@ void osqp_set_default_settings(OSQPSettings *s) {  // src/types.jl:138-143; SURV
 }
 
 const char *osqp_version(void) { return "0.6.2-b200"; }  // src/interface.jl:220
+
+c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int count) {
+  if (!work) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  const c_int have = 16 * (c_int)e.geom.grid;
+  CU_OK(cudaMemcpy(out, e.d.dbg, (size_t)std::min(count, have) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
 
 c_int osqp_b200_device_count(void) {
   int n = 0;
@@ -439,7 +508,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   cudaDeviceProp prop;
   CU_OK(cudaGetDeviceProperties(&prop, e.device));
   e.geom.block = env_int("OSQP_B200_BLOCK", 1024);
-  const int per_sm = max_coop_blocks_per_sm(e.geom.block);
+  const int per_sm = max_coop_blocks_per_sm(e.geom.block, 0);
   if (per_sm <= 0) {
     fprintf(stderr, "ERROR in osqp_setup: the sm_100a kernels cannot run on device %d (%s, sm_%d%d)\n", e.device,
             prop.name, prop.major, prop.minor);
@@ -467,15 +536,16 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   CU_OK(dalloc(e, &d.P.val, nnzP)); CU_OK(dalloc(e, &d.P.val0, nnzP));
   double **nvecs[] = {&d.q, &d.q0, &d.Pdiag, &d.D, &d.Dinv, &d.dtmp, &d.x, &d.xt, &d.dx, &d.r, &d.b, &d.uu,
                       &d.p, &d.s, &d.w, &d.Minv, &d.pol_x, &d.pol_rhs, &d.sol_x};
-  for (double **p : nvecs) CU_OK(dalloc(e, p, n));
+  for (double **p : nvecs) CU_OK(dalloc(e, p, (size_t)n + 8));  // +8: TMA tile copies round up to 16 B
   double **mvecs[] = {&d.l, &d.u, &d.l0, &d.u0, &d.rho_vec, &d.rho_inv, &d.E, &d.Einv, &d.etmp, &d.z, &d.y, &d.zt,
                       &d.dy, &d.wv, &d.t, &d.tr, &d.Ap, &d.pol_y, &d.pol_z, &d.pol_rho, &d.pol_b, &d.sol_y};
-  for (double **p : mvecs) CU_OK(dalloc(e, p, m));
+  for (double **p : mvecs) CU_OK(dalloc(e, p, (size_t)m + 8));
   CU_OK(dalloc(e, &d.ctype, m));
   CU_OK(dalloc(e, &d.m_start, e.geom.grid + 1));
   CU_OK(dalloc(e, &d.n_start, e.geom.grid + 1));
   CU_OK(dalloc(e, &d.bar, 2));
   CU_OK(dalloc(e, &d.red, (size_t)2 * kRedSlots * e.geom.grid));
+  CU_OK(dalloc(e, &d.dbg, (size_t)16 * e.geom.grid));
   CU_OK(dalloc(e, &d.state, 1));
   CU_OK(dalloc(e, &d.info, 1));
   CU_OK(dalloc(e, &e.d_pol, 1));
@@ -500,9 +570,71 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
 #undef H2D
   e.l0.assign(data->l, data->l + m);
   e.u0.assign(data->u, data->u + m);
+  std::vector<int> part_m, part_n;
   {
-    c_int rc = upload_partition(e, A_rowptr, At_rowptr, P_rowptr);
+    c_int rc = upload_partition(e, A_rowptr, At_rowptr, P_rowptr, part_m, part_n);
     if (rc) return rc;
+  }
+
+  // ---- column-blocked copies for the hot phases (engine.cuh BlkDev)
+  {
+    int rows_cap = 0;
+    for (int b = 0; b < e.geom.grid; b++)
+      rows_cap = std::max(rows_cap, (part_m[b + 1] - part_m[b]) + (part_n[b + 1] - part_n[b]));
+    rows_cap = (rows_cap + 15) & ~15;
+    const long long budget = (long long)prop.sharedMemPerBlockOptin - 8448 /* static RedSmem */ - 256;
+    const long long x_bytes = budget - 8LL * rows_cap;
+    int Wmax = (int)std::min<long long>(x_bytes / 8, 65536);
+    Wmax &= ~31;
+    d.blocked = env_int("OSQP_B200_BLOCKED", 1) && Wmax >= 2048;
+    if (d.blocked) {
+      auto pickW = [&](int cols) {
+        const int nb = std::max(1, (cols + Wmax - 1) / Wmax);
+        int W = (cols + nb - 1) / nb;
+        W = std::max(32, (W + 31) & ~31);
+        return W;
+      };
+      const int Wn = pickW(n), Wm = pickW(std::max(m, 1));
+      BlkHost hA, hP, hAt;
+      build_blocked(P_rowptr, P_col, n, n, Wn, hP);
+      { c_int rc = upload_blk(e, hP, n, n, d.Pb); if (rc) return rc; }
+      if (m > 0) {
+        build_blocked(A_rowptr, A_col, m, n, Wn, hA);
+        { c_int rc = upload_blk(e, hA, m, n, d.Ab); if (rc) return rc; }
+        build_blocked(At_rowptr, At_col, n, m, Wm, hAt);
+        { c_int rc = upload_blk(e, hAt, n, m, d.Atb); if (rc) return rc; }
+        // A' tiles: tiles_per_cb row ranges per column block, nnz-balanced inside the block
+        const int nbM = hAt.nb, per_cb = std::max(1, e.geom.grid / nbM);
+        std::vector<int> tcb, tr0, tr1;
+        for (int cb = 0; cb < nbM; cb++) {
+          const int *rp = hAt.rowptr.data() + (size_t)cb * (n + 1);
+          std::vector<long long> w(n + 1, 0);
+          for (int j = 0; j < n; j++) w[j + 1] = w[j] + (rp[j + 1] - rp[j]) + 2;
+          std::vector<int> st;
+          balanced_split(w, n, per_cb, st);
+          for (int t = 0; t < per_cb; t++) { tcb.push_back(cb); tr0.push_back(st[t]); tr1.push_back(st[t + 1]); }
+        }
+        // interleave so that tile t -> block t % grid spreads each column block over the whole grid
+        d.at_ntiles = (int)tcb.size();
+        CU_OK(dalloc(e, &d.at_tile_cb, tcb.size())); CU_OK(dalloc(e, &d.at_tile_r0, tcb.size()));
+        CU_OK(dalloc(e, &d.at_tile_r1, tcb.size()));
+        CU_OK(cudaMemcpyAsync(d.at_tile_cb, tcb.data(), tcb.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(cudaMemcpyAsync(d.at_tile_r0, tr0.data(), tr0.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(cudaMemcpyAsync(d.at_tile_r1, tr1.data(), tr1.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(cudaStreamSynchronize(e.stream));
+        CU_OK(dalloc(e, &d.partAt, (size_t)nbM * n + 8));
+      }
+      CU_OK(dalloc(e, &d.Pu, (size_t)n + 8));
+      d.smem_x_elems = std::max(Wn, m > 0 ? Wm : 0) + 2;
+      d.smem_x_elems = (d.smem_x_elems + 15) & ~15;
+      d.smem_rows = rows_cap;
+      e.geom.dyn_smem = 8ULL * ((size_t)d.smem_x_elems + d.smem_rows) + 64;
+      CU_OK(configure_dyn_smem(e.geom.dyn_smem));
+      if (max_coop_blocks_per_sm(e.geom.block, e.geom.dyn_smem) < 1) {
+        fprintf(stderr, "ERROR in osqp_setup: shared-memory tile of %zu bytes does not fit\n", e.geom.dyn_smem);
+        return 13;
+      }
+    }
   }
 
   // ---- state, scaling (a2), rho vector (a3), preconditioner, convexity probe
@@ -931,14 +1063,16 @@ c_int osqp_b200_set_pcg(OSQPWorkspace *work, c_float eta, c_float floor_rel, c_i
 
 c_int osqp_b200_spmv(OSQPWorkspace *work, c_int which, const c_float *in_host, c_float *out_host, c_int reps,
                      c_float *ms_per_rep) {
-  if (!work || which < 0 || which > 2 || reps < 1) return 1;
+  if (!work || which < 0 || (which > 2 && which < 10) || which > 12 || reps < 1) return 1;
   Engine &e = *E(work);
   DeviceGuard guard(e.device);
   const int n = e.d.n, m = e.d.m;
-  const int in_len = (which == 1) ? m : n, out_len = (which == 0) ? m : n;
+  const int wm = (int)(which % 10);
+  if (m == 0 && wm != 2) return 1;
+  const int in_len = (wm == 1) ? m : n, out_len = (wm == 0) ? m : n;
   // scratch: PCG vectors are free between solves (uu/w are n, t/tr are m)
-  double *din = (which == 1) ? e.d.tr : e.d.uu;
-  double *dout = (which == 0) ? e.d.t : e.d.w;
+  double *din = (wm == 1) ? e.d.tr : e.d.uu;
+  double *dout = (wm == 0) ? e.d.t : e.d.w;
   { c_int rc = upload_vector(e, din, in_host, in_len); if (rc) return rc; }
   CU_OK(launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream));  // warm-up
   CU_OK(cudaEventRecord(e.ev0, e.stream));

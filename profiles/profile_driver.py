@@ -38,7 +38,8 @@ for _ in range(args.solves):
 fp = C.POINTER(C.c_double)
 eng.osqp_b200_spmv.restype = C.c_longlong
 rng = np.random.default_rng(1)
-for which, ilen in ((0, args.n), (1, args.m), (2, args.n)):
+ap_which = ((0, args.n), (1, args.m), (2, args.n), (10, args.n), (11, args.m), (12, args.n))
+for which, ilen in ap_which:
     vin = rng.standard_normal(ilen)
     ms = C.c_double()
     eng.osqp_b200_spmv(mdl.workspace, C.c_longlong(which), vin.ctypes.data_as(fp), None, C.c_longlong(args.spmv_reps),

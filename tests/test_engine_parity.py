@@ -112,21 +112,25 @@ def test_scaling_vectors_match_oracle(pkg, engine_lib, oracle_lib):
     assert abs(ce.value - co.value) <= 1e-12 * co.value
 
 
-@pytest.mark.parametrize("which", [0, 1, 2])
-def test_spmv_kernels_match_oracle(pkg, engine_lib, oracle_lib, which):
-    n, m = 3000, 5000
-    prob = random_qp(n, m, 0.004, 33)
+@pytest.mark.parametrize("n,m,density", [(3000, 5000, 0.004), (60000, 70000, 0.0002)])
+@pytest.mark.parametrize("which", [0, 1, 2, 10, 11, 12])
+def test_spmv_kernels_match_oracle(pkg, engine_lib, oracle_lib, which, n, m, density):
+    # 0-2: hot-path format (column blocks staged in shared memory by TMA; 60000 x 70000 needs 3 blocks each
+    # way), 10-12: CSR + L1-gather path of the rare phases
+    prob = random_qp(n, m, density, 33)
     mdl = pkg.Model(lib=engine_lib)
     mdl.setup(**prob, verbose=False, scaling=0, sigma=1e-6)  # scaling off => resident matrices == inputs
     eng = pkg.load_library(engine_lib)
     ora = pkg.load_library(oracle_lib)
     fp = C.POINTER(C.c_double)
     rng = np.random.default_rng(4)
+    call = which
+    which = which % 10
     vin = rng.standard_normal(m if which == 1 else n)
     out = np.zeros(m if which == 0 else n)
     ms = C.c_double()
     eng.osqp_b200_spmv.restype = C.c_longlong
-    rc = eng.osqp_b200_spmv(mdl.workspace, C.c_longlong(which), vin.ctypes.data_as(fp), out.ctypes.data_as(fp),
+    rc = eng.osqp_b200_spmv(mdl.workspace, C.c_longlong(call), vin.ctypes.data_as(fp), out.ctypes.data_as(fp),
                             C.c_longlong(3), C.byref(ms))
     assert rc == 0 and ms.value > 0
     A = pkg.ManagedCcsc(prob["A"])
