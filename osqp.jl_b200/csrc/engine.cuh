@@ -41,6 +41,9 @@ struct BlkDev {
   unsigned short *col = nullptr; // column index local to the block
   double *val = nullptr;         // scaled values
   int *from_csr = nullptr;       // CSR position -> blocked position (value refresh after re-scaling)
+  // element span of the rows a thread block owns inside column block cb: [span[cb*grid+b], span[cb*grid+b+1])
+  // (owner passes of A and P); used to bulk-prefetch the next pass into L2
+  int *span = nullptr;
 };
 
 // Persistent solver state that survives between launches (device memory).
@@ -104,6 +107,7 @@ struct DevPtrs {
   double *partAt = nullptr;      // [Atb.nb][n] partial sums of A' w per column block
   int at_ntiles = 0;             // A' tiles (column block x row range), tile t is processed by block t % grid
   int *at_tile_cb = nullptr, *at_tile_r0 = nullptr, *at_tile_r1 = nullptr;
+  int *at_tile_lo = nullptr, *at_tile_hi = nullptr;  // element span of each tile in Atb.val / Atb.col
   int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged vector tile
   int smem_rows = 0;             // doubles of dynamic shared memory for per-row running sums
   // work partition: block b owns rows [m_start[b], m_start[b+1]) of A and [n_start[b], n_start[b+1]) of P/A'

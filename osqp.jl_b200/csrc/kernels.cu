@@ -24,6 +24,7 @@ constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
 constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
 constexpr double kDivisionTol = 1e-30;
 constexpr int kPrintInterval = 200;
+constexpr int kThreads = 512;  // threads per block of the cooperative kernels: 128 registers per thread
 
 constexpr long long ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4, ST_MAX_ITER = -2,
                     ST_PINF = -3, ST_DINF = -4, ST_TIME_LIMIT = -6, ST_NON_CVX = -7, ST_UNSOLVED = -10;
@@ -86,8 +87,10 @@ __device__ __forceinline__ void stage_init(Stage &S, const DevPtrs &d) {
 }
 
 // Copy `count` doubles from global `src` (16 B aligned, readable up to the next even count) into S.xs.
-// Caller guarantees every thread has finished reading the previous tile (a __syncthreads()).
-__device__ __forceinline__ void stage_tile(Stage &S, const double *src, int count) {
+// stage_issue: caller guarantees every thread has finished reading the previous tile (a __syncthreads()).
+// stage_wait : every thread, before the first read of S.xs.  Independent work (the first matrix loads of
+// the pass) goes between the two so the staging latency is hidden.
+__device__ __forceinline__ void stage_issue(Stage &S, const double *src, int count) {
   const unsigned bytes = ((unsigned)count * 8u + 15u) & ~15u;
   const unsigned mbar = smem_u32(S.mbar);
   if (threadIdx.x == 0) {
@@ -105,6 +108,9 @@ __device__ __forceinline__ void stage_tile(Stage &S, const double *src, int coun
                    : "memory");
     }
   }
+}
+__device__ __forceinline__ void stage_wait(Stage &S) {
+  const unsigned mbar = smem_u32(S.mbar);
   unsigned done = 0;
   while (!done) {
     asm volatile(
@@ -117,20 +123,23 @@ __device__ __forceinline__ void stage_tile(Stage &S, const double *src, int coun
 }
 
 // rows [r0, r1) of column block cb against the staged tile xs; epilogue(row, partial sum) on lane 0 of the group.
-// Software pipelined: a group of `lanes` threads owns rows r0+grp, r0+grp+ngrp, ... and keeps TWO rows'
-// (value, column) loads in flight in registers (kSlots strided elements each) while it reduces the row
-// before them; the row pointers are fetched two rows ahead.  With 1024 threads that is ~80 KB of matrix
-// stream in flight per SM at all times, which is what a ~1 us HBM round trip needs at 44 GB/s per SM;
-// the gather itself hits shared memory.  Rows longer than lanes*kSlots fall into a (non-pipelined) tail loop.
-constexpr int kSlots = 4;
+// Software pipelined in registers: a group of `lanes` threads owns rows r0+grp, r0+grp+ngrp, ... and keeps
+// kDepth rows' (value, column) loads in flight (kSlots strided elements each) while it reduces the oldest one;
+// row pointers are fetched one round (kDepth rows) ahead.  With 512 threads that is up to 160 B per lane =
+// 80 KB of matrix stream in flight per SM at all times.  `ready()` is called once after the first round of
+// loads has been issued and before the first gather: the wait for the staged x tile goes there, so the TMA
+// staging overlaps the first HBM round trip.  Rows longer than lanes*kSlots use a (non-pipelined) tail loop.
+constexpr int kSlots = 4, kDepth = 4;
 
-template <typename Epi>
-__device__ __forceinline__ void blk_rows(const BlkDev &B, int cb, int r0, int r1, const double *xs, Epi epi) {
+template <typename Ready, typename Epi>
+__device__ __forceinline__ void blk_rows(const BlkDev &B, int cb, int r0, int r1, const double *xs, Ready ready,
+                                         Epi epi) {
   const int lanes = B.lanes;
   const int tid = threadIdx.x, sub = tid & (lanes - 1), grp = tid / lanes, ngrp = blockDim.x / lanes;
   const int *rp = B.rowptr + (size_t)cb * (B.rows + 1);
   const double *__restrict__ val = B.val;
   const unsigned short *__restrict__ col = B.col;
+  const int round = kDepth * ngrp;
 
   auto load_rp = [&](int row, int &k0, int &k1) {
     const bool valid = row < r1;
@@ -157,24 +166,60 @@ __device__ __forceinline__ void blk_rows(const BlkDev &B, int cb, int r0, int r1
     if (sub == 0 && row < r1) epi(row, acc);
   };
 
-  int rowA = r0 + grp, rowB = rowA + ngrp;
-  int a0, a1, b0, b1;
-  load_rp(rowA, a0, a1);
-  load_rp(rowB, b0, b1);
-  double vA[kSlots], vB[kSlots];
-  unsigned cA[kSlots], cB[kSlots];
-  issue(a0, a1, vA, cA);
-  for (int base = r0; base < r1; base += 2 * ngrp) {  // trip count uniform over the block
-    issue(b0, b1, vB, cB);
-    int n0, n1;
-    load_rp(rowA + 2 * ngrp, n0, n1);
-    consume(rowA, a0, a1, vA, cA);
-    rowA += 2 * ngrp; a0 = n0; a1 = n1;
-    issue(a0, a1, vA, cA);
-    load_rp(rowB + 2 * ngrp, n0, n1);
-    consume(rowB, b0, b1, vB, cB);
-    rowB += 2 * ngrp; b0 = n0; b1 = n1;
+  int row[kDepth], k0[kDepth], k1[kDepth], k0n[kDepth], k1n[kDepth];
+  double v[kDepth][kSlots];
+  unsigned c[kDepth][kSlots];
+#pragma unroll
+  for (int dd = 0; dd < kDepth; dd++) {
+    row[dd] = r0 + grp + dd * ngrp;
+    load_rp(row[dd], k0[dd], k1[dd]);
   }
+#pragma unroll
+  for (int dd = 0; dd < kDepth; dd++) load_rp(row[dd] + round, k0n[dd], k1n[dd]);
+#pragma unroll
+  for (int dd = 0; dd < kDepth; dd++) issue(k0[dd], k1[dd], v[dd], c[dd]);
+  ready();
+  for (int base = r0; base < r1; base += round) {  // trip count uniform over the block
+#pragma unroll
+    for (int dd = 0; dd < kDepth; dd++) {
+      consume(row[dd], k0[dd], k1[dd], v[dd], c[dd]);
+      row[dd] += round;
+      k0[dd] = k0n[dd];
+      k1[dd] = k1n[dd];
+      issue(k0[dd], k1[dd], v[dd], c[dd]);
+      load_rp(row[dd] + round, k0n[dd], k1n[dd]);
+    }
+  }
+}
+
+// Fire-and-forget bulk prefetch of the element span [lo, hi) of a blocked matrix into L2
+// (cp.async.bulk.prefetch.L2): issued by one warp, one 16 B aligned piece per lane.  The consumers'
+// register loads of the next pass then see L2 latency instead of a loaded-HBM round trip.
+__device__ __forceinline__ void l2_prefetch_bytes(const void *ptr, long long bytes, int lane) {
+  if (bytes <= 0) return;
+  const unsigned long long a0 = (unsigned long long)ptr & ~15ull;
+  const unsigned long long a1 = ((unsigned long long)ptr + (unsigned long long)bytes + 15ull) & ~15ull;
+  unsigned long long piece = ((a1 - a0) / 32ull + 15ull) & ~15ull;
+  if (piece < 16ull) piece = 16ull;
+  const unsigned long long s = a0 + piece * (unsigned long long)lane;
+  if (s >= a1) return;
+  const unsigned long long e = (s + piece < a1) ? s + piece : a1;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s), "r"((unsigned)(e - s)) : "memory");
+}
+__device__ __forceinline__ void l2_prefetch_span(const BlkDev &B, int lo, int hi, int lane) {
+  l2_prefetch_bytes(B.val + lo, 8ll * (hi - lo), lane);
+  l2_prefetch_bytes(B.col + lo, 2ll * (hi - lo), lane);
+}
+// owner pass (column block cb of A and P) of this thread block; call from one full warp
+__device__ __forceinline__ void l2_prefetch_owner(const DevPtrs &d, int cb, int lane) {
+  const int pid = cb * (int)gridDim.x + (int)blockIdx.x;
+  if (d.m > 0) l2_prefetch_span(d.Ab, __ldg(d.Ab.span + pid), __ldg(d.Ab.span + pid + 1), lane);
+  l2_prefetch_span(d.Pb, __ldg(d.Pb.span + pid), __ldg(d.Pb.span + pid + 1), lane);
+}
+// first A' tile of this thread block
+__device__ __forceinline__ void l2_prefetch_at(const DevPtrs &d, int lane) {
+  const int t = blockIdx.x;
+  if (d.m > 0 && t < d.at_ntiles) l2_prefetch_span(d.Atb, __ldg(d.at_tile_lo + t), __ldg(d.at_tile_hi + t), lane);
 }
 
 // A' tiles (column block x row range) against `vec` (m): partial sums into d.partAt[cb][row]; dot(row, partial) on lane 0
@@ -184,10 +229,12 @@ __device__ __forceinline__ void at_tiles(Stage &S, const DevPtrs &d, const doubl
     const int cb = d.at_tile_cb[t], r0 = d.at_tile_r0[t], r1 = d.at_tile_r1[t];
     const int c0 = cb * d.Atb.W;
     const int cnt = (d.m - c0 < d.Atb.W) ? (d.m - c0) : d.Atb.W;
+    if (threadIdx.x < 32 && t + (int)gridDim.x < d.at_ntiles)
+      l2_prefetch_span(d.Atb, __ldg(d.at_tile_lo + t + gridDim.x), __ldg(d.at_tile_hi + t + gridDim.x), threadIdx.x);
     __syncthreads();
-    stage_tile(S, vec + c0, cnt);
+    stage_issue(S, vec + c0, cnt);
     double *out = d.partAt + (size_t)cb * d.n;
-    blk_rows(d.Atb, cb, r0, r1, S.xs, [&](int row, double acc) {
+    blk_rows(d.Atb, cb, r0, r1, S.xs, [&]() { stage_wait(S); }, [&](int row, double acc) {
       out[row] = acc;
       dot(row, acc);
     });
@@ -451,14 +498,24 @@ __device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const De
   while (rn > thresh && it < max_it) {
     double red1[1] = {0.0};
     // ---- phase A'
+    if (it == 0 && tid < 32) l2_prefetch_owner(d, 0, tid);
     for (int cb = 0; cb < nbN; cb++) {
       const int c0 = cb * d.Pb.W;
       const int cnt = (n - c0 < d.Pb.W) ? (n - c0) : d.Pb.W;
+      if (tid < 32) {  // next pass -> L2 while this one is reduced
+        if (cb + 1 < nbN) l2_prefetch_owner(d, cb + 1, tid);
+        else l2_prefetch_at(d, tid);
+      }
       __syncthreads();
-      stage_tile(S, v.uu + c0, cnt);
+      stage_issue(S, v.uu + c0, cnt);
       const bool first = (cb == 0), last = (cb == nbN - 1);
+      bool waited = false;
+      auto ready = [&]() {
+        if (!waited) stage_wait(S);
+        waited = true;
+      };
       if (d.m > 0)
-        blk_rows(d.Ab, cb, m0, m1, S.xs, [&](int row, double acc) {
+        blk_rows(d.Ab, cb, m0, m1, S.xs, ready, [&](int row, double acc) {
           const double sres = first ? acc : S.rowsum[row - m0] + acc;
           if (last) {
             v.t[row] = sres;
@@ -467,7 +524,7 @@ __device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const De
             S.rowsum[row - m0] = sres;
           }
         });
-      blk_rows(d.Pb, cb, n0, n1, S.xs, [&](int row, double acc) {
+      blk_rows(d.Pb, cb, n0, n1, S.xs, ready, [&](int row, double acc) {
         const double sres = first ? acc : S.rowsum[mrows + row - n0] + acc;
         if (last) {
           const double uj = v.uu[row];
@@ -480,7 +537,8 @@ __device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const De
     }
     if (d.m > 0) {
       grid_barrier(g);
-      // ---- phase B'
+      // ---- phase B' (the next iteration's first owner pass is prefetched speculatively)
+      if (tid < 32) l2_prefetch_owner(d, 0, tid);
       at_tiles(S, d, v.tr, [&](int row, double acc) { red1[0] += v.uu[row] * acc; });
     }
     reduce_and_barrier<1>(g, sm, red1, 0u);
@@ -681,7 +739,7 @@ __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho
 }
 
 // ------------------------------------------------------------------ the ADMM kernel
-__global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const SolveCfg c) {
+__global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, const SolveCfg c) {
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
@@ -715,6 +773,7 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
   long long it;
   for (it = 1; it <= c.max_iter; it++) {
     // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde)
+    if (d.blocked && !refresh && tid < 32) l2_prefetch_at(d, tid);
     for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
     if (refresh && d.m > 0) {
       for (int base = m0; base < m1; base += ngrpA) {
@@ -958,7 +1017,7 @@ __global__ void __launch_bounds__(1024, 1) admm_kernel(const DevPtrs d, const So
 // run CG on (P + sigma I) v = b for a pseudo-random b: CG's pivots p'(P+sigma I)p are the pivots
 // of the Lanczos tridiagonal, so a non-positive one appears as soon as the smallest Ritz value
 // crosses zero (exact after n steps; extreme eigenvalues converge first).
-__global__ void __launch_bounds__(1024, 1) pd_probe_kernel(const DevPtrs d, double sigma, int max_it) {
+__global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const DevPtrs d, double sigma, int max_it) {
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
@@ -1025,7 +1084,7 @@ __global__ void __launch_bounds__(1024, 1) pd_probe_kernel(const DevPtrs d, doub
 // the PCG above (rho := penalty on active rows, 0 elsewhere).  libosqp factorises the
 // delta-regularised KKT and applies `polish_refine_iter` refinement steps; both converge to
 // the same KKT point of the active-set QP.
-__global__ void __launch_bounds__(1024, 1) polish_kernel(const DevPtrs d, const PolishCfg c, const SolveCfg sc,
+__global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, const PolishCfg c, const SolveCfg sc,
                                                          PolishOut *out) {
   __shared__ RedSmem sm;
   Grid g;
@@ -1167,7 +1226,7 @@ __global__ void __launch_bounds__(1024, 1) polish_kernel(const DevPtrs d, const 
 
 // ------------------------------------------------------------------ standalone SpMV (profiling / parity)
 // which: 0  out = A in (m) | 1  out = A' in (n) | 2  out = (P + sigma I) in (n)
-__global__ void __launch_bounds__(1024, 1) spmv_kernel(const DevPtrs d, int which, const double *in, double *out,
+__global__ void __launch_bounds__(kThreads, 1) spmv_kernel(const DevPtrs d, int which, const double *in, double *out,
                                                        double sigma) {
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
@@ -1205,7 +1264,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_kernel(const DevPtrs d, int whic
 
 // Standalone SpMV on the column-blocked copies: exactly the phase code of pcg_run_blk (A / P: row owner over
 // the column blocks; A': tiles -> partials -> owner sum after one grid barrier).
-__global__ void __launch_bounds__(1024, 1) spmv_blk_kernel(const DevPtrs d, int which, const double *in, double *out,
+__global__ void __launch_bounds__(kThreads, 1) spmv_blk_kernel(const DevPtrs d, int which, const double *in, double *out,
                                                             double sigma) {
   Grid g;
   grid_init(g, d);
@@ -1214,6 +1273,7 @@ __global__ void __launch_bounds__(1024, 1) spmv_blk_kernel(const DevPtrs d, int 
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
   if (which == 1) {
+    if (tid < 32) l2_prefetch_at(d, tid);
     at_tiles(SG, d, in, [](int, double) {});
     grid_barrier(g);
     for (int j = n0 + tid; j < n1; j += nth) {
@@ -1231,11 +1291,18 @@ __global__ void __launch_bounds__(1024, 1) spmv_blk_kernel(const DevPtrs d, int 
   for (int cb = 0; cb < B.nb; cb++) {
     const int c0 = cb * B.W;
     const int cnt = (d.n - c0 < B.W) ? (d.n - c0) : B.W;
+    if (tid < 32) {
+      const int pid = cb * (int)gridDim.x + b;
+      if (cb == 0) l2_prefetch_span(B, __ldg(B.span + pid), __ldg(B.span + pid + 1), tid);
+      if (cb + 1 < B.nb) l2_prefetch_span(B, __ldg(B.span + pid + gridDim.x), __ldg(B.span + pid + gridDim.x + 1), tid);
+    }
     __syncthreads();
-    stage_tile(SG, in + c0, cnt);
-    if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
+    stage_issue(SG, in + c0, cnt);
     const bool first = (cb == 0), last = (cb == B.nb - 1);
-    blk_rows(B, cb, r0, r1, SG.xs, [&](int row, double acc) {
+    blk_rows(B, cb, r0, r1, SG.xs, [&]() {
+      stage_wait(SG);
+      if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
+    }, [&](int row, double acc) {
       const double sres = first ? acc : SG.rowsum[row - r0] + acc;
       if (last) out[row] = sres + (which == 2 ? sigma * in[row] : 0.0);
       else SG.rowsum[row - r0] = sres;

@@ -507,7 +507,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   // ---- launch geometry
   cudaDeviceProp prop;
   CU_OK(cudaGetDeviceProperties(&prop, e.device));
-  e.geom.block = env_int("OSQP_B200_BLOCK", 1024);
+  e.geom.block = std::min(512, env_int("OSQP_B200_BLOCK", 512));  // kernels.cu kThreads
   const int per_sm = max_coop_blocks_per_sm(e.geom.block, 0);
   if (per_sm <= 0) {
     fprintf(stderr, "ERROR in osqp_setup: the sm_100a kernels cannot run on device %d (%s, sm_%d%d)\n", e.device,
@@ -516,7 +516,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   }
   const int max_grid = std::min(kMaxBlocks, prop.multiProcessorCount * std::min(per_sm, env_int("OSQP_B200_BLOCKS_PER_SM", 1)));
   const long long work = 2 * nnzA + nnzP + 4LL * (n + m);
-  long long want = (work + 32767) / 32768;
+  long long want = (work + 16383) / 16384;
   int grid = (int)std::max(1LL, std::min<long long>(want, max_grid));
   grid = env_int("OSQP_B200_GRID", grid);
   e.geom.grid = std::max(1, std::min(grid, max_grid));
@@ -596,23 +596,39 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
       };
       const int Wn = pickW(n), Wm = pickW(std::max(m, 1));
       BlkHost hA, hP, hAt;
+      auto upload_span = [&](const BlkHost &h, int rows, const std::vector<int> &part, BlkDev &bd) -> c_int {
+        const int G = e.geom.grid;
+        std::vector<int> span((size_t)h.nb * G + 1);
+        for (int cb = 0; cb < h.nb; cb++)
+          for (int b = 0; b < G; b++) span[(size_t)cb * G + b] = h.rowptr[(size_t)cb * (rows + 1) + part[b]];
+        span[(size_t)h.nb * G] = (int)h.col.size();
+        CU_OK(dalloc(e, &bd.span, span.size()));
+        CU_OK(cudaMemcpyAsync(bd.span, span.data(), span.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(cudaStreamSynchronize(e.stream));
+        return 0;
+      };
       build_blocked(P_rowptr, P_col, n, n, Wn, hP);
       { c_int rc = upload_blk(e, hP, n, n, d.Pb); if (rc) return rc; }
+      { c_int rc = upload_span(hP, n, part_n, d.Pb); if (rc) return rc; }
       if (m > 0) {
         build_blocked(A_rowptr, A_col, m, n, Wn, hA);
         { c_int rc = upload_blk(e, hA, m, n, d.Ab); if (rc) return rc; }
+        { c_int rc = upload_span(hA, m, part_m, d.Ab); if (rc) return rc; }
         build_blocked(At_rowptr, At_col, n, m, Wm, hAt);
         { c_int rc = upload_blk(e, hAt, n, m, d.Atb); if (rc) return rc; }
         // A' tiles: tiles_per_cb row ranges per column block, nnz-balanced inside the block
         const int nbM = hAt.nb, per_cb = std::max(1, e.geom.grid / nbM);
-        std::vector<int> tcb, tr0, tr1;
+        std::vector<int> tcb, tr0, tr1, tlo, thi;
         for (int cb = 0; cb < nbM; cb++) {
           const int *rp = hAt.rowptr.data() + (size_t)cb * (n + 1);
           std::vector<long long> w(n + 1, 0);
           for (int j = 0; j < n; j++) w[j + 1] = w[j] + (rp[j + 1] - rp[j]) + 2;
           std::vector<int> st;
           balanced_split(w, n, per_cb, st);
-          for (int t = 0; t < per_cb; t++) { tcb.push_back(cb); tr0.push_back(st[t]); tr1.push_back(st[t + 1]); }
+          for (int t = 0; t < per_cb; t++) {
+            tcb.push_back(cb); tr0.push_back(st[t]); tr1.push_back(st[t + 1]);
+            tlo.push_back(rp[st[t]]); thi.push_back(rp[st[t + 1]]);
+          }
         }
         // interleave so that tile t -> block t % grid spreads each column block over the whole grid
         d.at_ntiles = (int)tcb.size();
@@ -621,6 +637,9 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
         CU_OK(cudaMemcpyAsync(d.at_tile_cb, tcb.data(), tcb.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
         CU_OK(cudaMemcpyAsync(d.at_tile_r0, tr0.data(), tr0.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
         CU_OK(cudaMemcpyAsync(d.at_tile_r1, tr1.data(), tr1.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(dalloc(e, &d.at_tile_lo, tlo.size())); CU_OK(dalloc(e, &d.at_tile_hi, thi.size()));
+        CU_OK(cudaMemcpyAsync(d.at_tile_lo, tlo.data(), tlo.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+        CU_OK(cudaMemcpyAsync(d.at_tile_hi, thi.data(), thi.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
         CU_OK(cudaStreamSynchronize(e.stream));
         CU_OK(dalloc(e, &d.partAt, (size_t)nbM * n + 8));
       }
