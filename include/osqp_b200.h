@@ -55,6 +55,12 @@ c_int osqp_b200_get_scaling(OSQPWorkspace *work, c_float *D, c_float *E, c_float
 /* Debug: per-block globaltimer probes written by the last blocked osqp_b200_spmv launch ([grid][16]). */
 c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int count);
 
+/* Host-only self-test of the tile-stream storage (DESIGN.md "tile streams"): builds the stream of a CSR matrix
+ * with the setup code and replays the device reduction on the CPU; y_out = M x.  Returns 0, 2 if the builder
+ * declines the matrix (padding / capacity), > 2 on a format violation.  Needs no GPU. */
+c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
+                                const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio);
+
 c_int osqp_b200_device_count(void);
 
 #ifdef __cplusplus

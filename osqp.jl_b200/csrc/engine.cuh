@@ -28,22 +28,36 @@ struct CsrDev {
   int lanes = 32;          // lanes cooperating on one row (power of two <= 32)
 };
 
-// Column-blocked copy of a CSR matrix for the hot SpMV phases: the dense input vector is staged
-// one block of W columns at a time in shared memory (TMA bulk copy) and gathered from there, so
-// column indices are block-local 16-bit values (10 B / nnz instead of 12) and no random 8-byte
-// gather ever reaches L2.  Block cb holds, row by row, the entries with cb*W <= col < (cb+1)*W.
-struct BlkDev {
-  int nb = 0;                    // number of column blocks
-  int W = 0;                     // columns per block (multiple of 32, W*8 bytes fit in shared memory)
-  int rows = 0, cols = 0;
-  int lanes = 8;                 // threads cooperating on one row segment
-  int *rowptr = nullptr;         // [nb][rows+1] absolute positions into col/val (block-major storage)
-  unsigned short *col = nullptr; // column index local to the block
-  double *val = nullptr;         // scaled values
-  int *from_csr = nullptr;       // CSR position -> blocked position (value refresh after re-scaling)
-  // element span of the rows a thread block owns inside column block cb: [span[cb*grid+b], span[cb*grid+b+1])
-  // (owner passes of A and P); used to bulk-prefetch the next pass into L2
-  int *span = nullptr;
+// Tile stream: the hot-path storage of a (row-stacked) sparse matrix M (rows x cols) that is multiplied with a
+// dense vector of length `cols` once per phase (S_A = [A; P] against an n-vector, S_T = A' against an m-vector).
+//
+//   * 2-D split.  The columns are cut into `ngroups` groups; every thread block belongs to ONE group and stages
+//     only that group's slice of the dense vector (<= kSliceMax doubles) in shared memory with TMA bulk copies, so
+//     the vector is pulled from L2 once per phase per SM.
+//   * Inside a group the rows are cut into contiguous, nnz-balanced ranges, one per warp (kWarps per block).  A
+//     warp's entries are stored contiguously, row by row.  There is no row pointer: an entry is (fp64 value, u16
+//     word = column local to the group slice); every row segment is padded with zero entries to a multiple of 4 (a
+//     "quad"), and bit 15 of the LAST word of a quad marks the end of a row.  Each lane streams whole quads with two
+//     16 B value loads and one 8 B column load, perfectly coalesced and aligned: 10 B per stored entry.
+//   * A lane sums its quad; row sums are formed with a warp-segmented scan over the per-lane flags (carry across
+//     chunks) and written straight to part[group][row].  The owner blocks add the `ngroups` partial vectors in the
+//     element-wise phase that follows the next grid barrier (fixed order -> run-to-run deterministic).
+constexpr int kWarps = 16;          // warps per thread block of the cooperative kernels (kThreads / 32)
+constexpr int kSliceMax = 27648;    // doubles per staged slice (216 KB); local columns are 15-bit
+
+struct TileStreamDev {
+  int rows = 0, cols = 0;        // stacked rows, length of the gathered vector
+  int ngroups = 0;
+  int pf_chunks = 0;             // chunks (32 quads = 1280 B) a warp prefetches into L2 ahead of its register loads
+  long long nelem = 0;           // padded stream length in entries (multiple of 4)
+  double *val = nullptr;         // [nelem] scaled values (zero on padding)
+  unsigned short *cf = nullptr;  // [nelem] local column; bit 15 of every 4th word: row ends with this quad
+  int *from_csr = nullptr;       // stacked CSR position -> stream position (value refresh after re-scaling)
+  int *blk_group = nullptr;      // [grid]
+  int *grp_col0 = nullptr;       // [ngroups + 1] column range of each group (multiples of 32)
+  int *w_row0 = nullptr;         // [grid * kWarps] first stacked row of warp i
+  int *w_q0 = nullptr;           // [grid * kWarps + 1] quads [w_q0[i], w_q0[i+1]) are the stream of warp i
+  double *part = nullptr;        // [ngroups][rows] partial row sums of the last phase
 };
 
 // Persistent solver state that survives between launches (device memory).
@@ -100,16 +114,11 @@ struct DevPtrs {
   double *pol_y = nullptr, *pol_z = nullptr, *pol_rho = nullptr, *pol_b = nullptr;  // m
   // results
   double *sol_x = nullptr, *sol_y = nullptr;
-  // column-blocked copies for the hot phases (blocked == 0: fall back to the CSR + L1 gather path)
+  // tile streams for the hot phases (blocked == 0: fall back to the CSR + L1 gather path everywhere)
   int blocked = 0;
-  BlkDev Ab, Pb, Atb;
+  TileStreamDev SA, ST;          // [A; P] against an n-vector, A' against an m-vector
   double *Pu = nullptr;          // n: P u of the current PCG iteration
-  double *partAt = nullptr;      // [Atb.nb][n] partial sums of A' w per column block
-  int at_ntiles = 0;             // A' tiles (column block x row range), tile t is processed by block t % grid
-  int *at_tile_cb = nullptr, *at_tile_r0 = nullptr, *at_tile_r1 = nullptr;
-  int *at_tile_lo = nullptr, *at_tile_hi = nullptr;  // element span of each tile in Atb.val / Atb.col
-  int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged vector tile
-  int smem_rows = 0;             // doubles of dynamic shared memory for per-row running sums
+  int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged slice
   // work partition: block b owns rows [m_start[b], m_start[b+1]) of A and [n_start[b], n_start[b+1]) of P/A'
   int *m_start = nullptr, *n_start = nullptr;
   // grid barrier + reductions

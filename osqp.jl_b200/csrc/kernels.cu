@@ -59,185 +59,178 @@ __device__ __forceinline__ unsigned ld_stream(const unsigned short *p) {
   return v;
 }
 
-// ------------------------------------------------------------------ shared-memory staging of the dense vector tile (TMA)
-// One elected thread arms an mbarrier with the byte count and issues 1-D bulk async copies
-// (cp.async.bulk.shared.global -> UBLKCP); every thread then waits on the mbarrier phase.
-struct Stage {
-  double *xs;                  // staged tile of the gathered vector
-  double *rowsum;              // running row sums across column blocks (row-owner phases)
-  unsigned long long *mbar;
+// ------------------------------------------------------------------ tile streams (engine.cuh TileStreamDev)
+// Shared-memory staging of the gathered vector slice: one elected thread arms an mbarrier with the byte count and
+// issues 1-D bulk async copies (cp.async.bulk.shared.global -> UBLKCP); every warp waits on the mbarrier right
+// before its first gather, after its first matrix loads are already in flight.
+struct Slice {
+  unsigned xs;       // shared-space address of the staged slice
+  unsigned mbar;     // shared-space address of its mbarrier
   unsigned parity;
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void stage_init(Stage &S, const DevPtrs &d) {
+__device__ __forceinline__ void slice_init(Slice &S, const DevPtrs &d) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
-  S.xs = reinterpret_cast<double *>(dyn_smem);
-  S.rowsum = S.xs + d.smem_x_elems;
-  S.mbar = reinterpret_cast<unsigned long long *>(S.rowsum + d.smem_rows);
+  S.xs = smem_u32(dyn_smem);
+  S.mbar = S.xs + 8u * (unsigned)d.smem_x_elems;
   S.parity = 0;
   if (d.blocked) {
     if (threadIdx.x == 0) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(S.mbar)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(S.mbar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
   }
 }
 
-// Copy `count` doubles from global `src` (16 B aligned, readable up to the next even count) into S.xs.
-// stage_issue: caller guarantees every thread has finished reading the previous tile (a __syncthreads()).
-// stage_wait : every thread, before the first read of S.xs.  Independent work (the first matrix loads of
-// the pass) goes between the two so the staging latency is hidden.
-__device__ __forceinline__ void stage_issue(Stage &S, const double *src, int count) {
-  const unsigned bytes = ((unsigned)count * 8u + 15u) & ~15u;
-  const unsigned mbar = smem_u32(S.mbar);
-  if (threadIdx.x == 0) {
-    // the tile was written with ordinary stores by other blocks before the grid barrier:
-    // order those generic-proxy writes before the async-proxy (TMA) reads
-    asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
-    const unsigned dst = smem_u32(S.xs);
-    const char *g = reinterpret_cast<const char *>(src);
-    for (unsigned off = 0; off < bytes; off += 32768u) {
-      const unsigned chunk = (bytes - off < 32768u) ? (bytes - off) : 32768u;
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                       dst + off),
-                   "l"(g + off), "r"(chunk), "r"(mbar)
-                   : "memory");
-    }
-  }
-}
-__device__ __forceinline__ void stage_wait(Stage &S) {
-  const unsigned mbar = smem_u32(S.mbar);
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
   unsigned done = 0;
   while (!done) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(done)
-        : "r"(mbar), "r"(S.parity)
+        : "r"(mbar), "r"(parity)
         : "memory");
   }
-  S.parity ^= 1u;
 }
 
-// rows [r0, r1) of column block cb against the staged tile xs; epilogue(row, partial sum) on lane 0 of the group.
-// Software pipelined in registers: a group of `lanes` threads owns rows r0+grp, r0+grp+ngrp, ... and keeps
-// kDepth rows' (value, column) loads in flight (kSlots strided elements each) while it reduces the oldest one;
-// row pointers are fetched one round (kDepth rows) ahead.  With 512 threads that is up to 160 B per lane =
-// 80 KB of matrix stream in flight per SM at all times.  `ready()` is called once after the first round of
-// loads has been issued and before the first gather: the wait for the staged x tile goes there, so the TMA
-// staging overlaps the first HBM round trip.  Rows longer than lanes*kSlots use a (non-pipelined) tail loop.
-constexpr int kSlots = 4, kDepth = 4;
-
-template <typename Ready, typename Epi>
-__device__ __forceinline__ void blk_rows(const BlkDev &B, int cb, int r0, int r1, const double *xs, Ready ready,
-                                         Epi epi) {
-  const int lanes = B.lanes;
-  const int tid = threadIdx.x, sub = tid & (lanes - 1), grp = tid / lanes, ngrp = blockDim.x / lanes;
-  const int *rp = B.rowptr + (size_t)cb * (B.rows + 1);
-  const double *__restrict__ val = B.val;
-  const unsigned short *__restrict__ col = B.col;
-  const int round = kDepth * ngrp;
-
-  auto load_rp = [&](int row, int &k0, int &k1) {
-    const bool valid = row < r1;
-    k0 = valid ? ld_stream(rp + row) : 0;
-    k1 = valid ? ld_stream(rp + row + 1) : 0;
-  };
-  auto issue = [&](int k0, int k1, double (&v)[kSlots], unsigned (&c)[kSlots]) {
-#pragma unroll
-    for (int t = 0; t < kSlots; t++) {
-      const int kk = k0 + sub + t * lanes;
-      const bool in = kk < k1;
-      v[t] = in ? ld_stream(val + kk) : 0.0;
-      c[t] = in ? ld_stream(col + kk) : 0u;
-    }
-  };
-  auto consume = [&](int row, int k0, int k1, double (&v)[kSlots], unsigned (&c)[kSlots]) {
-    double acc = 0.0;
-#pragma unroll
-    for (int t = 0; t < kSlots; t++)
-      if (k0 + sub + t * lanes < k1) acc += v[t] * xs[c[t]];
-    for (int kk = k0 + sub + kSlots * lanes; kk < k1; kk += lanes) acc += ld_stream(val + kk) * xs[ld_stream(col + kk)];
-    __syncwarp();
-    for (int o = lanes >> 1; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, lanes);
-    if (sub == 0 && row < r1) epi(row, acc);
-  };
-
-  int row[kDepth], k0[kDepth], k1[kDepth], k0n[kDepth], k1n[kDepth];
-  double v[kDepth][kSlots];
-  unsigned c[kDepth][kSlots];
-#pragma unroll
-  for (int dd = 0; dd < kDepth; dd++) {
-    row[dd] = r0 + grp + dd * ngrp;
-    load_rp(row[dd], k0[dd], k1[dd]);
-  }
-#pragma unroll
-  for (int dd = 0; dd < kDepth; dd++) load_rp(row[dd] + round, k0n[dd], k1n[dd]);
-#pragma unroll
-  for (int dd = 0; dd < kDepth; dd++) issue(k0[dd], k1[dd], v[dd], c[dd]);
-  ready();
-  for (int base = r0; base < r1; base += round) {  // trip count uniform over the block
-#pragma unroll
-    for (int dd = 0; dd < kDepth; dd++) {
-      consume(row[dd], k0[dd], k1[dd], v[dd], c[dd]);
-      row[dd] += round;
-      k0[dd] = k0n[dd];
-      k1[dd] = k1n[dd];
-      issue(k0[dd], k1[dd], v[dd], c[dd]);
-      load_rp(row[dd] + round, k0n[dd], k1n[dd]);
-    }
-  }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+  return v;
 }
 
-// Fire-and-forget bulk prefetch of the element span [lo, hi) of a blocked matrix into L2
-// (cp.async.bulk.prefetch.L2): issued by one warp, one 16 B aligned piece per lane.  The consumers'
-// register loads of the next pass then see L2 latency instead of a loaded-HBM round trip.
-__device__ __forceinline__ void l2_prefetch_bytes(const void *ptr, long long bytes, int lane) {
-  if (bytes <= 0) return;
+// Fire-and-forget bulk prefetch of [ptr, ptr + bytes) into L2 (16 B aligned pieces).
+__device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes) {
   const unsigned long long a0 = (unsigned long long)ptr & ~15ull;
-  const unsigned long long a1 = ((unsigned long long)ptr + (unsigned long long)bytes + 15ull) & ~15ull;
-  unsigned long long piece = ((a1 - a0) / 32ull + 15ull) & ~15ull;
-  if (piece < 16ull) piece = 16ull;
-  const unsigned long long s = a0 + piece * (unsigned long long)lane;
-  if (s >= a1) return;
-  const unsigned long long e = (s + piece < a1) ? s + piece : a1;
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(s), "r"((unsigned)(e - s)) : "memory");
-}
-__device__ __forceinline__ void l2_prefetch_span(const BlkDev &B, int lo, int hi, int lane) {
-  l2_prefetch_bytes(B.val + lo, 8ll * (hi - lo), lane);
-  l2_prefetch_bytes(B.col + lo, 2ll * (hi - lo), lane);
-}
-// owner pass (column block cb of A and P) of this thread block; call from one full warp
-__device__ __forceinline__ void l2_prefetch_owner(const DevPtrs &d, int cb, int lane) {
-  const int pid = cb * (int)gridDim.x + (int)blockIdx.x;
-  if (d.m > 0) l2_prefetch_span(d.Ab, __ldg(d.Ab.span + pid), __ldg(d.Ab.span + pid + 1), lane);
-  l2_prefetch_span(d.Pb, __ldg(d.Pb.span + pid), __ldg(d.Pb.span + pid + 1), lane);
-}
-// first A' tile of this thread block
-__device__ __forceinline__ void l2_prefetch_at(const DevPtrs &d, int lane) {
-  const int t = blockIdx.x;
-  if (d.m > 0 && t < d.at_ntiles) l2_prefetch_span(d.Atb, __ldg(d.at_tile_lo + t), __ldg(d.at_tile_hi + t), lane);
+  const unsigned long long a1 = ((unsigned long long)ptr + bytes + 15ull) & ~15ull;
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
 }
 
-// A' tiles (column block x row range) against `vec` (m): partial sums into d.partAt[cb][row]; dot(row, partial) on lane 0
-template <typename Dot>
-__device__ __forceinline__ void at_tiles(Stage &S, const DevPtrs &d, const double *vec, Dot dot) {
-  for (int t = blockIdx.x; t < d.at_ntiles; t += gridDim.x) {
-    const int cb = d.at_tile_cb[t], r0 = d.at_tile_r0[t], r1 = d.at_tile_r1[t];
-    const int c0 = cb * d.Atb.W;
-    const int cnt = (d.m - c0 < d.Atb.W) ? (d.m - c0) : d.Atb.W;
-    if (threadIdx.x < 32 && t + (int)gridDim.x < d.at_ntiles)
-      l2_prefetch_span(d.Atb, __ldg(d.at_tile_lo + t + gridDim.x), __ldg(d.at_tile_hi + t + gridDim.x), threadIdx.x);
-    __syncthreads();
-    stage_issue(S, vec + c0, cnt);
-    double *out = d.partAt + (size_t)cb * d.n;
-    blk_rows(d.Atb, cb, r0, r1, S.xs, [&]() { stage_wait(S); }, [&](int row, double acc) {
-      out[row] = acc;
-      dot(row, acc);
-    });
+constexpr int kDepth = 4;  // chunks (one quad per lane, 40 B) of matrix stream in flight per lane
+
+struct QuadSlot {
+  double v0, v1, v2, v3;
+  unsigned c01, c23;
+};
+
+// pv / pc: this lane's byte addresses inside the value / column streams
+__device__ __forceinline__ void quad_load(QuadSlot &q, const char *pv, const char *pc, bool active) {
+  q.v0 = q.v1 = q.v2 = q.v3 = 0.0;
+  q.c01 = q.c23 = 0u;
+  if (active) {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(q.v0), "=d"(q.v1) : "l"(pv));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(q.v2), "=d"(q.v3) : "l"(pv + 16));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(q.c01), "=r"(q.c23) : "l"(pc));
+  }
+}
+
+// Warm L2 with the head of this warp's stream of T; call before the grid barrier that precedes the phase.
+__device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
+  const int lane = threadIdx.x & 31, wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
+  const int q0 = __ldg(T.w_q0 + wid), total = __ldg(T.w_q0 + wid + 1) - q0;
+  if (lane < T.pf_chunks && lane * 32 < total) {
+    const unsigned quads = (unsigned)min(32, total - lane * 32);
+    l2_prefetch(T.val + 4ll * (q0 + lane * 32), quads * 32u);
+    l2_prefetch(T.cf + 4ll * (q0 + lane * 32), quads * 8u);
+  }
+}
+
+// One phase of  part[group][row] = sum over the block's column group of M[row, :] vec  for the rows of every warp.
+// Must be entered by all threads of the block after a grid barrier (the previous users of the slice are done and
+// `vec` is complete and visible).
+__device__ __noinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  const int grp = __ldg(T.blk_group + b);
+  const unsigned parity = S.parity;
+  S.parity ^= 1u;
+  if (tid == 0) {
+    // the vector was written with ordinary stores by other blocks before the grid barrier: order those
+    // generic-proxy writes before the async-proxy (TMA) reads
+    asm volatile("fence.proxy.async;" ::: "memory");
+    const int col0 = __ldg(T.grp_col0 + grp), ncols = __ldg(T.grp_col0 + grp + 1) - col0;
+    const unsigned bytes = ((unsigned)ncols * 8u + 15u) & ~15u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.mbar), "r"(bytes) : "memory");
+    const char *g = reinterpret_cast<const char *>(vec + col0);
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+      const unsigned chunk = (bytes - off < 32768u) ? (bytes - off) : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       S.xs + off),
+                   "l"(g + off), "r"(chunk), "r"(S.mbar)
+                   : "memory");
+    }
+  }
+  const int wid = b * kWarps + warp;
+  const int q0 = __ldg(T.w_q0 + wid), L = __ldg(T.w_q0 + wid + 1) - q0;  // quads of this warp
+  if (L <= 0) {
+    // warp 0 still drains the mbarrier it armed so that the next phase never re-arms a pending one
+    if (warp == 0) mbar_wait(S.mbar, parity);
+    return;
+  }
+  double *__restrict__ out = T.part + (size_t)grp * T.rows + __ldg(T.w_row0 + wid);
+  const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * (q0 + lane);
+  const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
+  const char *pf_v = reinterpret_cast<const char *>(T.val) + 32ll * q0;
+  const char *pf_c = reinterpret_cast<const char *>(T.cf) + 8ll * q0;
+  const int pf = T.pf_chunks;
+  const unsigned xs = S.xs;
+  const unsigned lt = (1u << lane) - 1u;
+  int left = L - lane;   // > 0: this lane still has a quad in the chunk being issued
+  int issued = 0;        // chunks issued so far
+  int rdone = 0;
+  double carry = 0.0;
+
+  auto issue = [&](QuadSlot &q) {
+    quad_load(q, pv, pc, left > 0);
+    pv += 1024;
+    pc += 256;
+    left -= 32;
+    if ((issued & 3) == 0 && lane == 0 && pf > 0) {  // every 4th chunk: the 4 chunks `pf` ahead go to L2
+      const int pq = (issued + pf) * 32;
+      if (pq < L) {
+        const unsigned quads = (unsigned)min(128, L - pq);
+        l2_prefetch(pf_v + 32ll * pq, quads * 32u);
+        l2_prefetch(pf_c + 8ll * pq, quads * 8u);
+      }
+    }
+    issued++;
+  };
+  auto consume = [&](const QuadSlot &q) {
+    const double x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+    const double x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    double inc = q.v0 * x0;
+    inc = fma(q.v1, x1, inc);
+    inc = fma(q.v2, x2, inc);
+    inc = fma(q.v3, x3, inc);
+    const bool flag = (q.c23 >> 31) != 0u;  // a row ends with this lane's quad
+    const unsigned bal = __ballot_sync(0xffffffffu, flag);
+    const unsigned below = bal & lt;
+    const int h = 32 - __clz(below);  // first lane of the row this lane's quad belongs to (0 if none ended below)
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, dlt);
+      if (lane - dlt >= h) inc += t;
+    }
+    if (below == 0u) inc += carry;  // the row started in an earlier chunk
+    if (flag) out[rdone + __popc(below)] = inc;
+    const double last = __shfl_sync(0xffffffffu, inc, 31);
+    carry = (bal >> 31) ? 0.0 : last;
+    rdone += __popc(bal);
+  };
+
+  QuadSlot slot[kDepth];
+#pragma unroll
+  for (int k = 0; k < kDepth; k++) issue(slot[k]);
+  mbar_wait(S.mbar, parity);  // the slice has landed (the first matrix loads are already in flight)
+  const int nchunks = (L + 31) >> 5;
+  for (int base = 0; base < nchunks; base += kDepth) {
+#pragma unroll
+    for (int k = 0; k < kDepth; k++) {
+      if (base + k < nchunks) consume(slot[k]);
+      issue(slot[k]);
+    }
   }
 }
 
@@ -481,67 +474,55 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, const DevPtrs &d, cons
   return it;
 }
 
-// Same recurrence on the column-blocked matrices with the gathered vector staged in shared memory:
-//   phase A': every block walks the column blocks of the n-dimension (stage uu[cb] once, use it for
-//             its rows of A *and* of P; running row sums in shared memory) -> t, tr = rho.*t, Pu
-//   phase B': one A' tile (column block x row range) per block, tr[cb] staged -> partAt[cb][:]
-//   phase V : w = Pu + sigma uu + sum_cb partAt[cb]; delta was already accumulated tile by tile
-__device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const DevPtrs &d, const PcgVecs &v,
-                                        const double *rho_vec, const double *Minv, double sigma, double *xvec,
-                                        double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
-                                        int m1, int n0, int n1) {
+// Owner-side sum of the per-group partial row sums of a tile-stream phase (fixed order).
+__device__ __forceinline__ double part_sum(const TileStreamDev &T, int row) {
+  double a = T.part[row];
+  for (int g = 1; g < T.ngroups; g++) a += T.part[(size_t)g * T.rows + row];
+  return a;
+}
+
+// Same recurrence on the tile streams (engine.cuh TileStreamDev), 4 grid barriers per iteration:
+//   phase A : [A; P] uu  -> partial row sums per column group                      | barrier
+//   phase C : owners: t = sum of partials, tr = rho .* t, Pu; delta = uu'P uu + sigma |uu|^2 + t'tr | reduce + barrier
+//   phase B : A' tr      -> partial row sums per column group                      | barrier
+//   phase V : owners: w = Pu + sigma uu + sum of partials, vector recurrences      | reduce + barrier
+__device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, const DevPtrs &d, const PcgVecs &v,
+                                           const double *rho_vec, const double *Minv, double sigma, double *xvec,
+                                           double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
+                                           int m1, int n0, int n1) {
   const int tid = threadIdx.x, nth = blockDim.x;
-  const int nbN = d.Pb.nb, nbM = (d.m > 0) ? d.Atb.nb : 0, n = d.n;
-  const int mrows = m1 - m0;
+  const int m = d.m;
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
   while (rn > thresh && it < max_it) {
+    // ---- phase A
+    stream_phase(S, d.SA, v.uu);
+    if (m > 0) stream_prefetch_head(d.ST);
+    grid_barrier(g);
+    // ---- phase C
     double red1[1] = {0.0};
-    // ---- phase A'
-    if (it == 0 && tid < 32) l2_prefetch_owner(d, 0, tid);
-    for (int cb = 0; cb < nbN; cb++) {
-      const int c0 = cb * d.Pb.W;
-      const int cnt = (n - c0 < d.Pb.W) ? (n - c0) : d.Pb.W;
-      if (tid < 32) {  // next pass -> L2 while this one is reduced
-        if (cb + 1 < nbN) l2_prefetch_owner(d, cb + 1, tid);
-        else l2_prefetch_at(d, tid);
-      }
-      __syncthreads();
-      stage_issue(S, v.uu + c0, cnt);
-      const bool first = (cb == 0), last = (cb == nbN - 1);
-      bool waited = false;
-      auto ready = [&]() {
-        if (!waited) stage_wait(S);
-        waited = true;
-      };
-      if (d.m > 0)
-        blk_rows(d.Ab, cb, m0, m1, S.xs, ready, [&](int row, double acc) {
-          const double sres = first ? acc : S.rowsum[row - m0] + acc;
-          if (last) {
-            v.t[row] = sres;
-            v.tr[row] = rho_vec[row] * sres;
-          } else {
-            S.rowsum[row - m0] = sres;
-          }
-        });
-      blk_rows(d.Pb, cb, n0, n1, S.xs, ready, [&](int row, double acc) {
-        const double sres = first ? acc : S.rowsum[mrows + row - n0] + acc;
-        if (last) {
-          const double uj = v.uu[row];
-          d.Pu[row] = sres;
-          red1[0] += uj * (sres + sigma * uj);
-        } else {
-          S.rowsum[mrows + row - n0] = sres;
-        }
-      });
+    for (int i = m0 + tid; i < m1; i += nth) {
+      const double ti = part_sum(d.SA, i);
+      const double tri = rho_vec[i] * ti;
+      v.t[i] = ti;
+      v.tr[i] = tri;
+      red1[0] += ti * tri;
     }
-    if (d.m > 0) {
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double pu = part_sum(d.SA, m + j);
+      const double uj = v.uu[j];
+      d.Pu[j] = pu;
+      red1[0] += uj * (pu + sigma * uj);
+    }
+    if (m > 0) {
+      reduce_and_barrier<1>(g, sm, red1, 0u);
+      // ---- phase B
+      stream_phase(S, d.ST, v.tr);
+      stream_prefetch_head(d.SA);
       grid_barrier(g);
-      // ---- phase B' (the next iteration's first owner pass is prefetched speculatively)
-      if (tid < 32) l2_prefetch_owner(d, 0, tid);
-      at_tiles(S, d, v.tr, [&](int row, double acc) { red1[0] += v.uu[row] * acc; });
+    } else {
+      reduce_and_barrier<1>(g, sm, red1, 0u);
     }
-    reduce_and_barrier<1>(g, sm, red1, 0u);
     const double delta = red1[0];
     double beta, alpha;
     if (it == 0) {
@@ -551,13 +532,13 @@ __device__ __noinline__ int pcg_run_blk(Grid &g, RedSmem &sm, Stage &S, const De
       beta = gamma / gamma_old;
       alpha = gamma / (delta - beta * gamma / a_old);
     }
-    if (!(alpha > 0.0) || !isfinite(alpha)) break;
+    if (!(alpha > 0.0) || !isfinite(alpha)) break;  // breakdown: p'Kp <= 0 or exact convergence
     // ---- phase V
     double red2[2] = {0.0, 0.0};
     for (int j = n0 + tid; j < n1; j += nth) {
       const double uj = v.uu[j];
       double wj = d.Pu[j] + sigma * uj;
-      for (int cb = 0; cb < nbM; cb++) wj += d.partAt[(size_t)cb * n + j];
+      if (m > 0) wj += part_sum(d.ST, j);
       const double pj = (it == 0) ? uj : uj + beta * v.p[j];
       const double sj = (it == 0) ? wj : wj + beta * v.s[j];
       v.p[j] = pj;
@@ -743,8 +724,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
-  Stage SG;
-  stage_init(SG, d);
+  Slice SG;
+  slice_init(SG, d);
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
   const int lanesA = d.A.lanes, lanesN = d.At.lanes;
@@ -773,7 +754,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   long long it;
   for (it = 1; it <= c.max_iter; it++) {
     // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde)
-    if (d.blocked && !refresh && tid < 32) l2_prefetch_at(d, tid);
+    if (d.blocked && !refresh && d.m > 0) stream_prefetch_head(d.ST);
     for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
     if (refresh && d.m > 0) {
       for (int base = m0; base < m1; base += ngrpA) {
@@ -796,13 +777,12 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     if (d.blocked && !refresh) {
       // steady state: A' wv through the staged tiles, then the element-wise part on the owner block
       if (d.m > 0) {
-        at_tiles(SG, d, d.wv, [](int, double) {});
+        stream_phase(SG, d.ST, d.wv);
+        stream_prefetch_head(d.SA);
         grid_barrier(g);
       }
-      const int nbM = (d.m > 0) ? d.Atb.nb : 0;
       for (int j = n0 + tid; j < n1; j += nth) {
-        double acc = 0.0;
-        for (int cb = 0; cb < nbM; cb++) acc += d.partAt[(size_t)cb * d.n + j];
+        const double acc = (d.m > 0) ? part_sum(d.ST, j) : 0.0;
         const double bj = c.sigma * d.x[j] - d.q[j] + acc;
         const double rj = d.r[j] + (bj - d.b[j]);
         d.b[j] = bj;
@@ -854,8 +834,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
       // (r0 measures how far the system moved since the last solve), floored at roundoff level
       const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
-      const int ncg = d.blocked ? pcg_run_blk(g, sm, SG, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
-                                              red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                                                 red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
                                 : pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
                                           thresh, c.pcg_max_iter, m0, m1, n0, n1);
       cg_total += ncg;
@@ -1089,8 +1069,8 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, co
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
-  Stage SG;
-  stage_init(SG, d);
+  Slice SG;
+  slice_init(SG, d);
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
   const int lanesA = d.A.lanes, lanesN = d.At.lanes;
@@ -1163,8 +1143,8 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, co
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
-    cg_total += d.blocked ? pcg_run_blk(g, sm, SG, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
-                                        red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+    cg_total += d.blocked ? pcg_run_stream(g, sm, SG, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
+                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
                           : pcg_run(g, sm, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1],
                                     thresh, c.pcg_max_iter, m0, m1, n0, n1);
     // multiplier step on active rows: y += penalty (A x - b)
@@ -1262,53 +1242,40 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_kernel(const DevPtrs d, int 
   }
 }
 
-// Standalone SpMV on the column-blocked copies: exactly the phase code of pcg_run_blk (A / P: row owner over
-// the column blocks; A': tiles -> partials -> owner sum after one grid barrier).
-__global__ void __launch_bounds__(kThreads, 1) spmv_blk_kernel(const DevPtrs d, int which, const double *in, double *out,
-                                                            double sigma) {
+// Standalone SpMV on the tile streams: exactly the phase code of pcg_run_stream (stream phase -> grid barrier ->
+// owner sum of the partials).  which 0 and 2 both run the [A; P] stream; the requested half is written out.
+__global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs d, int which, const double *in,
+                                                                  double *out, double sigma) {
   Grid g;
   grid_init(g, d);
-  Stage SG;
-  stage_init(SG, d);
+  Slice SG;
+  slice_init(SG, d);
   const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x;
   const int m0 = d.m_start[b], m1 = d.m_start[b + 1], n0 = d.n_start[b], n1 = d.n_start[b + 1];
-  if (which == 1) {
-    if (tid < 32) l2_prefetch_at(d, tid);
-    at_tiles(SG, d, in, [](int, double) {});
-    grid_barrier(g);
-    for (int j = n0 + tid; j < n1; j += nth) {
-      double acc = 0.0;
-      for (int cb = 0; cb < d.Atb.nb; cb++) acc += d.partAt[(size_t)cb * d.n + j];
-      out[j] = acc;
-    }
-    return;
-  }
-  const BlkDev &B = (which == 0) ? d.Ab : d.Pb;
-  const int r0 = (which == 0) ? m0 : n0, r1 = (which == 0) ? m1 : n1;
+  const TileStreamDev &T = (which == 1) ? d.ST : d.SA;
+  // globaltimer probes per block: 0 start | 1 after the first grid barrier | 2 first / 3 last warp done with its
+  // stream | 4 block done | 5 after the second grid barrier
   unsigned long long *probe = d.dbg + (size_t)b * 16;
-  int np = 0;
-  if (tid == 0) probe[np++] = globaltimer_ns();
-  for (int cb = 0; cb < B.nb; cb++) {
-    const int c0 = cb * B.W;
-    const int cnt = (d.n - c0 < B.W) ? (d.n - c0) : B.W;
-    if (tid < 32) {
-      const int pid = cb * (int)gridDim.x + b;
-      if (cb == 0) l2_prefetch_span(B, __ldg(B.span + pid), __ldg(B.span + pid + 1), tid);
-      if (cb + 1 < B.nb) l2_prefetch_span(B, __ldg(B.span + pid + gridDim.x), __ldg(B.span + pid + gridDim.x + 1), tid);
-    }
-    __syncthreads();
-    stage_issue(SG, in + c0, cnt);
-    const bool first = (cb == 0), last = (cb == B.nb - 1);
-    blk_rows(B, cb, r0, r1, SG.xs, [&]() {
-      stage_wait(SG);
-      if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
-    }, [&](int row, double acc) {
-      const double sres = first ? acc : SG.rowsum[row - r0] + acc;
-      if (last) out[row] = sres + (which == 2 ? sigma * in[row] : 0.0);
-      else SG.rowsum[row - r0] = sres;
-    });
-    __syncthreads();
-    if (tid == 0 && np < 15) probe[np++] = globaltimer_ns();
+  if (tid == 0) { probe[0] = globaltimer_ns(); probe[2] = ~0ull; probe[3] = 0ull; }
+  stream_prefetch_head(T);
+  grid_barrier(g);
+  if (tid == 0) probe[1] = globaltimer_ns();
+  stream_phase(SG, T, in);
+  if ((tid & 31) == 0) {
+    const unsigned long long t = globaltimer_ns();
+    atomicMin(probe + 2, t);
+    atomicMax(probe + 3, t);
+  }
+  __syncthreads();
+  if (tid == 0) probe[4] = globaltimer_ns();
+  grid_barrier(g);
+  if (tid == 0) probe[5] = globaltimer_ns();
+  if (which == 0) {
+    for (int i = m0 + tid; i < m1; i += nth) out[i] = part_sum(d.SA, i);
+  } else if (which == 1) {
+    for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.ST, j);
+  } else {
+    for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.SA, d.m + j) + sigma * in[j];
   }
 }
 
@@ -1524,14 +1491,14 @@ __global__ void k_scatter(double *dst, const double *vals, const long long *idx,
   }
 }
 
-// blocked copies <- scaled CSR values
+// tile streams <- scaled CSR values (padding entries stay zero)
 __global__ void k_fill_blocked(const DevPtrs d) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
   for (long long k = tid; k < d.A.nnz; k += nth) {
-    d.Ab.val[d.Ab.from_csr[k]] = d.A.val[k];
-    d.Atb.val[d.Atb.from_csr[k]] = d.At.val[k];
+    d.SA.val[d.SA.from_csr[k]] = d.A.val[k];
+    d.ST.val[d.ST.from_csr[k]] = d.At.val[k];
   }
-  for (long long k = tid; k < d.P.nnz; k += nth) d.Pb.val[d.Pb.from_csr[k]] = d.P.val[k];
+  for (long long k = tid; k < d.P.nnz; k += nth) d.SA.val[d.SA.from_csr[d.A.nnz + k]] = d.P.val[k];
 }
 
 inline int ew_grid(long long work) {
@@ -1617,13 +1584,13 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
     spmv_kernel<<<g.grid, g.block, 0, st>>>(d, which % 10, in, out, sigma);
     return cudaGetLastError();
   }
-  return coop_launch(spmv_blk_kernel, g, st, d, which, in, out, sigma);
+  return coop_launch(spmv_stream_kernel, g, st, d, which, in, out, sigma);
 }
 
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
   cudaError_t e = cudaFuncSetAttribute(admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(spmv_blk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  e = cudaFuncSetAttribute(spmv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
 }

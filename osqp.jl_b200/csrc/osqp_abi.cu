@@ -225,63 +225,150 @@ void balanced_split(const std::vector<long long> &w_prefix, int rows, int parts,
   start[parts] = rows;
 }
 
-// Column-blocked copy of a host CSR matrix (engine.cuh BlkDev): block-major storage, 16-bit local columns.
-struct BlkHost {
-  int nb = 0, W = 0;
-  std::vector<int> rowptr, from_csr;
-  std::vector<unsigned short> col;
+// Host-side construction of a tile stream (engine.cuh TileStreamDev) from row-stacked CSR matrices that share the
+// column space.  `mats[k]` = (rowptr, col, rows) of the k-th stacked matrix; CSR positions are stacked likewise.
+struct CsrRef {
+  const std::vector<int> *rowptr, *col;
+  int rows;
 };
-void build_blocked(const std::vector<int> &rowptr, const std::vector<int> &col, int rows, int cols, int W,
-                   BlkHost &out) {
-  const int nb = std::max(1, (cols + W - 1) / W);
-  out.nb = nb;
-  out.W = W;
-  const long long nnz = rowptr[rows];
-  out.rowptr.assign((size_t)nb * (rows + 1), 0);
-  out.from_csr.resize(nnz);
-  out.col.resize(nnz);
-  // count per (block, row)
-  for (int r = 0; r < rows; r++)
-    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) out.rowptr[(size_t)(col[k] / W) * (rows + 1) + r + 1]++;
-  long long run = 0;
-  for (int cb = 0; cb < nb; cb++) {
-    int *rp = out.rowptr.data() + (size_t)cb * (rows + 1);
-    rp[0] = (int)run;
-    for (int r = 0; r < rows; r++) {
-      const int cnt = rp[r + 1];
-      rp[r + 1] = rp[r] + cnt;
+struct TileStreamHost {
+  int rows = 0, cols = 0, ngroups = 0;
+  long long nelem = 0, nnz = 0;
+  std::vector<unsigned short> cf;
+  std::vector<int> from_csr, blk_group, grp_col0, w_row0, w_q0;
+  int max_slice = 0;
+};
+
+// false: the stream does not pay off for this matrix (too much padding) -> CSR path
+bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int ngroups, TileStreamHost &T) {
+  int rows = 0;
+  long long nnz = 0;
+  for (const CsrRef &M : mats) { rows += M.rows; nnz += (*M.rowptr)[M.rows]; }
+  T.rows = rows; T.cols = cols; T.ngroups = ngroups; T.nnz = nnz;
+  if (ngroups > grid || ngroups < 1) return false;
+  // column groups (boundaries are multiples of 32 so every TMA source stays 16 B aligned)
+  const int Wg = (((cols + ngroups - 1) / ngroups) + 31) & ~31;
+  if (Wg > kSliceMax || Wg > 32768) return false;
+  T.max_slice = Wg;
+  T.grp_col0.resize(ngroups + 1);
+  for (int g = 0; g <= ngroups; g++) T.grp_col0[g] = std::min(cols, g * Wg);
+  // entries per (row, group)
+  std::vector<int> cnt((size_t)rows * ngroups, 0);
+  {
+    int r0 = 0;
+    for (const CsrRef &M : mats) {
+      for (int r = 0; r < M.rows; r++)
+        for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) cnt[(size_t)(r0 + r) * ngroups + (*M.col)[k] / Wg]++;
+      r0 += M.rows;
     }
-    run = rp[rows];
   }
-  std::vector<int> fill((size_t)nb * rows);
-  for (int cb = 0; cb < nb; cb++)
-    for (int r = 0; r < rows; r++) fill[(size_t)cb * rows + r] = out.rowptr[(size_t)cb * (rows + 1) + r];
-  for (int r = 0; r < rows; r++)
-    for (int k = rowptr[r]; k < rowptr[r + 1]; k++) {
-      const int cb = col[k] / W;
-      const int pos = fill[(size_t)cb * rows + r]++;
-      out.from_csr[k] = pos;
-      out.col[pos] = (unsigned short)(col[k] - cb * W);
+  // quads of a row inside a group (a row without entries there still costs one zero quad)
+  auto quads_of = [](int c) { return std::max(1, (c + 3) >> 2); };
+  std::vector<long long> gw(ngroups, 0);
+  std::vector<long long> wpre((size_t)ngroups * (rows + 1), 0);
+  long long stored = 0;
+  for (int g = 0; g < ngroups; g++) {
+    long long *wp = wpre.data() + (size_t)g * (rows + 1);
+    for (int r = 0; r < rows; r++) wp[r + 1] = wp[r] + quads_of(cnt[(size_t)r * ngroups + g]);
+    gw[g] = wp[rows];
+    stored += 4 * gw[g];
+  }
+  if (nnz > 0 && (double)stored > 1.35 * (double)nnz + 4096.0) return false;  // padding would dominate
+  if (stored > 2147483000LL) return false;
+  // thread blocks per group, proportional to the stored quads (every group gets at least one)
+  std::vector<int> nblk(ngroups, 1);
+  {
+    const int left = grid - ngroups;
+    std::vector<double> frac(ngroups);
+    int used = 0;
+    for (int g = 0; g < ngroups; g++) {
+      const double want = (double)left * (double)gw[g] / (double)std::max<long long>(1, stored / 4);
+      nblk[g] += (int)want;
+      used += (int)want;
+      frac[g] = want - (int)want;
     }
+    for (int k = used; k < left; k++) {
+      int best = 0;
+      for (int g = 1; g < ngroups; g++) if (frac[g] > frac[best]) best = g;
+      nblk[best]++;
+      frac[best] = -1.0;
+    }
+  }
+  T.blk_group.assign(grid, 0);
+  T.w_row0.assign((size_t)grid * kWarps, 0);
+  T.w_q0.assign((size_t)grid * kWarps + 1, 0);
+  std::vector<int> w_row1((size_t)grid * kWarps, 0);
+  // warp row ranges: contiguous and weight-balanced inside each group
+  int b0 = 0;
+  for (int g = 0; g < ngroups; g++) {
+    const long long *wp = wpre.data() + (size_t)g * (rows + 1);
+    const int nw = nblk[g] * kWarps;
+    int r = 0;
+    for (int w = 0; w < nw; w++) {
+      const int wid = b0 * kWarps + w, left_w = nw - w;
+      const long long target = wp[r] + (gw[g] - wp[r] + left_w - 1) / left_w;
+      int r1 = r;
+      while (r1 < rows && (r1 == r || wp[r1 + 1] <= target)) r1++;
+      if (w == nw - 1) r1 = rows;
+      T.w_row0[wid] = r;
+      w_row1[wid] = r1;
+      r = r1;
+    }
+    for (int bb = 0; bb < nblk[g]; bb++) T.blk_group[b0 + bb] = g;
+    b0 += nblk[g];
+  }
+  // positions: warp by warp, row by row; every row segment is a whole number of quads
+  std::vector<int> seg_start((size_t)rows * ngroups, 0);
+  long long pos = 0;
+  for (int wid = 0; wid < grid * kWarps; wid++) {
+    const int g = T.blk_group[wid / kWarps];
+    T.w_q0[wid] = (int)(pos / 4);
+    for (int r = T.w_row0[wid]; r < w_row1[wid]; r++) {
+      const size_t si = (size_t)r * ngroups + g;
+      seg_start[si] = (int)pos;
+      pos += 4 * quads_of(cnt[si]);
+    }
+  }
+  T.w_q0[(size_t)grid * kWarps] = (int)(pos / 4);
+  T.nelem = pos;
+  T.cf.assign((size_t)pos + 8, 0);
+  T.from_csr.resize(nnz);
+  std::vector<int> cursor(seg_start);
+  {
+    int r0 = 0;
+    long long k0 = 0;
+    for (const CsrRef &M : mats) {
+      for (int r = 0; r < M.rows; r++)
+        for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) {
+          const int c = (*M.col)[k], g = c / Wg;
+          const int p = cursor[(size_t)(r0 + r) * ngroups + g]++;
+          T.cf[p] = (unsigned short)(c - g * Wg);
+          T.from_csr[k0 + k] = p;
+        }
+      r0 += M.rows;
+      k0 += (*M.rowptr)[M.rows];
+    }
+  }
+  for (size_t si = 0; si < (size_t)rows * ngroups; si++) T.cf[seg_start[si] + 4 * quads_of(cnt[si]) - 1] |= 0x8000u;
+  return true;
 }
 
-c_int upload_blk(Engine &e, const BlkHost &h, int rows, int cols, BlkDev &b) {
-  const long long nnz = (long long)h.col.size();
-  b.nb = h.nb; b.W = h.W; b.rows = rows; b.cols = cols;
-  const double avg = (double)nnz / std::max(1.0, (double)rows * h.nb);
-  int l = 1;
-  while (l < 32 && (double)l * 4.0 < avg) l <<= 1;
-  b.lanes = env_int("OSQP_B200_BLK_LANES", l);
-  CU_OK(dalloc(e, &b.rowptr, h.rowptr.size()));
-  CU_OK(dalloc(e, &b.col, (size_t)nnz + 8));
-  CU_OK(dalloc(e, &b.val, (size_t)nnz + 8));
-  CU_OK(dalloc(e, &b.from_csr, (size_t)nnz));
-  CU_OK(cudaMemcpyAsync(b.rowptr, h.rowptr.data(), h.rowptr.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-  if (nnz > 0) {
-    CU_OK(cudaMemcpyAsync(b.col, h.col.data(), nnz * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
-    CU_OK(cudaMemcpyAsync(b.from_csr, h.from_csr.data(), nnz * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-  }
-  CU_OK(cudaStreamSynchronize(e.stream));
+c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
+  t.rows = h.rows; t.cols = h.cols; t.ngroups = h.ngroups; t.nelem = h.nelem;
+  t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 8))) & ~3;
+  CU_OK(dalloc(e, &t.val, (size_t)h.nelem + 8));
+  CU_OK(dalloc(e, &t.cf, (size_t)h.nelem + 8));
+  CU_OK(dalloc(e, &t.from_csr, (size_t)h.nnz));
+  CU_OK(dalloc(e, &t.part, (size_t)h.ngroups * h.rows + 8));
+#define UP(dst, vec)                                                                                         \
+  CU_OK(dalloc(e, &dst, (vec).size()));                                                                      \
+  CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
+  UP(t.blk_group, h.blk_group); UP(t.grp_col0, h.grp_col0); UP(t.w_row0, h.w_row0); UP(t.w_q0, h.w_q0);
+#undef UP
+  CU_OK(cudaMemcpyAsync(t.cf, h.cf.data(), (size_t)h.nelem * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
+  if (h.nnz > 0)
+    CU_OK(cudaMemcpyAsync(t.from_csr, h.from_csr.data(), (size_t)h.nnz * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+  CU_OK(cudaStreamSynchronize(e.stream));  // the host vectors go out of scope
   return 0;
 }
 
@@ -364,8 +451,10 @@ void print_setup_header(const Engine &e) {
          e.st.polish ? "on" : "off", e.st.warm_start ? "on" : "off");
 }
 
+// algorithmic bytes of one SpMV in the engine's own storage (DESIGN.md "bytes model"): fp64 value + 16-bit local
+// column per non-zero, the gathered vector read once, the result written once
 double spmv_bytes(long long nnz, long long rows, long long cols) {
-  return 12.0 * (double)nnz + 4.0 * (double)(rows + 1) + 8.0 * (double)cols + 8.0 * (double)rows;
+  return 10.0 * (double)nnz + 8.0 * (double)cols + 8.0 * (double)rows;
 }
 
 c_int upload_vector(Engine &e, double *dst, const c_float *src, long long count) {
@@ -395,6 +484,72 @@ c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int c
   DeviceGuard guard(e.device);
   const c_int have = 16 * (c_int)e.geom.grid;
   CU_OK(cudaMemcpy(out, e.d.dbg, (size_t)std::min(count, have) * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// Host-only check of the tile-stream format (no GPU needed): builds the stream of one CSR matrix exactly as
+// osqp_setup does and replays the device algorithm of kernels.cu stream_phase lane by lane (quads, per-lane row-end
+// flags, rank by flag count, segmented scan with the carry across chunks) on the CPU.  y_out = M x.
+c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
+                                const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio) {
+  std::vector<int> rp(rows + 1), ci(rowptr[rows]);
+  for (c_int r = 0; r <= rows; r++) rp[r] = (int)rowptr[r];
+  for (c_int k = 0; k < rowptr[rows]; k++) ci[k] = (int)col[k];
+  TileStreamHost T;
+  std::vector<CsrRef> mats{CsrRef{&rp, &ci, (int)rows}};
+  if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, T)) return 2;
+  if (padding_ratio) *padding_ratio = T.nnz ? (double)T.nelem / (double)T.nnz : 1.0;
+  std::vector<double> sv((size_t)T.nelem + 8, 0.0);
+  for (long long k = 0; k < T.nnz; k++) sv[T.from_csr[k]] = val[k];
+  std::vector<double> part((size_t)T.ngroups * rows, 0.0);
+  std::vector<char> written((size_t)T.ngroups * rows, 0);
+  for (int wid = 0; wid < (int)grid * kWarps; wid++) {
+    const int grp = T.blk_group[wid / kWarps];
+    const int q0 = T.w_q0[wid], L = T.w_q0[wid + 1] - q0;
+    if (L <= 0) continue;
+    const double *xs = x + T.grp_col0[grp];
+    const int slice = T.grp_col0[grp + 1] - T.grp_col0[grp];
+    double *out = part.data() + (size_t)grp * rows + T.w_row0[wid];
+    char *wr = written.data() + (size_t)grp * rows + T.w_row0[wid];
+    int rdone = 0;
+    double carry = 0.0;
+    for (int cc = 0; cc < L; cc += 32) {
+      double run = carry;
+      int nflag = 0;
+      for (int lane = 0; lane < 32; lane++) {
+        double acc = 0.0;
+        bool flag = false;
+        if (cc + lane < L) {
+          const long long e = 4ll * (q0 + cc + lane);
+          for (int t = 0; t < 4; t++) {
+            const unsigned w = T.cf[e + t];
+            const int lc = (int)(w & 0x7fffu);
+            if ((w & 0x8000u) && t != 3) return 4;  // only the last word of a quad may carry the flag
+            if (sv[e + t] != 0.0 && lc >= slice) return 5;
+            acc = (t == 0) ? sv[e] * xs[lc] : std::fma(sv[e + t], xs[lc], acc);
+          }
+          flag = (T.cf[e + 3] & 0x8000u) != 0;
+        }
+        run += acc;
+        if (flag) {
+          if (T.w_row0[wid] + rdone + nflag >= rows) return 6;
+          out[rdone + nflag] = run;
+          wr[rdone + nflag]++;
+          nflag++;
+          run = 0.0;
+        }
+      }
+      carry = run;
+      rdone += nflag;
+    }
+    if (carry != 0.0) return 8;  // the last quad of a warp's stream must close its row
+  }
+  for (size_t i = 0; i < written.size(); i++) if (written[i] != 1) return 9;
+  for (c_int r = 0; r < rows; r++) {
+    double a = part[r];
+    for (int g = 1; g < T.ngroups; g++) a += part[(size_t)g * rows + r];
+    y_out[r] = a;
+  }
   return 0;
 }
 
@@ -576,82 +731,43 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     if (rc) return rc;
   }
 
-  // ---- column-blocked copies for the hot phases (engine.cuh BlkDev)
+  // ---- tile streams for the hot phases (engine.cuh TileStreamDev)
   {
-    int rows_cap = 0;
-    for (int b = 0; b < e.geom.grid; b++)
-      rows_cap = std::max(rows_cap, (part_m[b + 1] - part_m[b]) + (part_n[b + 1] - part_n[b]));
-    rows_cap = (rows_cap + 15) & ~15;
-    const long long budget = (long long)prop.sharedMemPerBlockOptin - 8448 /* static RedSmem */ - 256;
-    const long long x_bytes = budget - 8LL * rows_cap;
-    int Wmax = (int)std::min<long long>(x_bytes / 8, 65536);
-    Wmax &= ~31;
-    d.blocked = env_int("OSQP_B200_BLOCKED", 1) && Wmax >= 2048;
-    if (d.blocked) {
-      auto pickW = [&](int cols) {
-        const int nb = std::max(1, (cols + Wmax - 1) / Wmax);
-        int W = (cols + nb - 1) / nb;
-        W = std::max(32, (W + 31) & ~31);
-        return W;
-      };
-      const int Wn = pickW(n), Wm = pickW(std::max(m, 1));
-      BlkHost hA, hP, hAt;
-      auto upload_span = [&](const BlkHost &h, int rows, const std::vector<int> &part, BlkDev &bd) -> c_int {
-        const int G = e.geom.grid;
-        std::vector<int> span((size_t)h.nb * G + 1);
-        for (int cb = 0; cb < h.nb; cb++)
-          for (int b = 0; b < G; b++) span[(size_t)cb * G + b] = h.rowptr[(size_t)cb * (rows + 1) + part[b]];
-        span[(size_t)h.nb * G] = (int)h.col.size();
-        CU_OK(dalloc(e, &bd.span, span.size()));
-        CU_OK(cudaMemcpyAsync(bd.span, span.data(), span.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(cudaStreamSynchronize(e.stream));
-        return 0;
-      };
-      build_blocked(P_rowptr, P_col, n, n, Wn, hP);
-      { c_int rc = upload_blk(e, hP, n, n, d.Pb); if (rc) return rc; }
-      { c_int rc = upload_span(hP, n, part_n, d.Pb); if (rc) return rc; }
-      if (m > 0) {
-        build_blocked(A_rowptr, A_col, m, n, Wn, hA);
-        { c_int rc = upload_blk(e, hA, m, n, d.Ab); if (rc) return rc; }
-        { c_int rc = upload_span(hA, m, part_m, d.Ab); if (rc) return rc; }
-        build_blocked(At_rowptr, At_col, n, m, Wm, hAt);
-        { c_int rc = upload_blk(e, hAt, n, m, d.Atb); if (rc) return rc; }
-        // A' tiles: tiles_per_cb row ranges per column block, nnz-balanced inside the block
-        const int nbM = hAt.nb, per_cb = std::max(1, e.geom.grid / nbM);
-        std::vector<int> tcb, tr0, tr1, tlo, thi;
-        for (int cb = 0; cb < nbM; cb++) {
-          const int *rp = hAt.rowptr.data() + (size_t)cb * (n + 1);
-          std::vector<long long> w(n + 1, 0);
-          for (int j = 0; j < n; j++) w[j + 1] = w[j] + (rp[j + 1] - rp[j]) + 2;
-          std::vector<int> st;
-          balanced_split(w, n, per_cb, st);
-          for (int t = 0; t < per_cb; t++) {
-            tcb.push_back(cb); tr0.push_back(st[t]); tr1.push_back(st[t + 1]);
-            tlo.push_back(rp[st[t]]); thi.push_back(rp[st[t + 1]]);
-          }
-        }
-        // interleave so that tile t -> block t % grid spreads each column block over the whole grid
-        d.at_ntiles = (int)tcb.size();
-        CU_OK(dalloc(e, &d.at_tile_cb, tcb.size())); CU_OK(dalloc(e, &d.at_tile_r0, tcb.size()));
-        CU_OK(dalloc(e, &d.at_tile_r1, tcb.size()));
-        CU_OK(cudaMemcpyAsync(d.at_tile_cb, tcb.data(), tcb.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(cudaMemcpyAsync(d.at_tile_r0, tr0.data(), tr0.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(cudaMemcpyAsync(d.at_tile_r1, tr1.data(), tr1.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(dalloc(e, &d.at_tile_lo, tlo.size())); CU_OK(dalloc(e, &d.at_tile_hi, thi.size()));
-        CU_OK(cudaMemcpyAsync(d.at_tile_lo, tlo.data(), tlo.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(cudaMemcpyAsync(d.at_tile_hi, thi.data(), thi.size() * sizeof(int), cudaMemcpyHostToDevice, e.stream));
-        CU_OK(cudaStreamSynchronize(e.stream));
-        CU_OK(dalloc(e, &d.partAt, (size_t)nbM * n + 8));
+    d.blocked = 0;
+    const long long smem_budget = (long long)prop.sharedMemPerBlockOptin - 8448 /* static RedSmem */ - 512;
+    const int slice_cap = std::min<long long>(std::min(kSliceMax, env_int("OSQP_B200_SLICE", kSliceMax)),
+                                              (smem_budget - 128) / 8);
+    auto groups_for = [&](int cols) {
+      int gmin = std::max(1, (cols + slice_cap - 1) / slice_cap);
+      return std::max(gmin, env_int("OSQP_B200_GROUPS", 0));
+    };
+    const bool want = env_int("OSQP_B200_BLOCKED", 1) != 0 && e.geom.grid >= 8 && (nnzA + nnzP) >= 200000;
+    if (want) {
+      TileStreamHost hA, hT;
+      std::vector<CsrRef> matsA;
+      if (m > 0) matsA.push_back(CsrRef{&A_rowptr, &A_col, m});
+      matsA.push_back(CsrRef{&P_rowptr, &P_col, n});
+      std::vector<CsrRef> matsT{CsrRef{&At_rowptr, &At_col, n}};
+      bool ok = build_tile_stream(matsA, n, e.geom.grid, groups_for(n), hA);
+      if (ok && m > 0) ok = build_tile_stream(matsT, m, e.geom.grid, groups_for(m), hT);
+      if (ok) {
+        const int slice = std::max(hA.max_slice, m > 0 ? hT.max_slice : 0);
+        d.smem_x_elems = (slice + 2 + 15) & ~15;
+        e.geom.dyn_smem = 8ULL * (size_t)d.smem_x_elems + 64;
+        ok = (long long)e.geom.dyn_smem <= smem_budget;
       }
-      CU_OK(dalloc(e, &d.Pu, (size_t)n + 8));
-      d.smem_x_elems = std::max(Wn, m > 0 ? Wm : 0) + 2;
-      d.smem_x_elems = (d.smem_x_elems + 15) & ~15;
-      d.smem_rows = rows_cap;
-      e.geom.dyn_smem = 8ULL * ((size_t)d.smem_x_elems + d.smem_rows) + 64;
-      CU_OK(configure_dyn_smem(e.geom.dyn_smem));
-      if (max_coop_blocks_per_sm(e.geom.block, e.geom.dyn_smem) < 1) {
-        fprintf(stderr, "ERROR in osqp_setup: shared-memory tile of %zu bytes does not fit\n", e.geom.dyn_smem);
-        return 13;
+      if (ok) {
+        { c_int rc = upload_tile_stream(e, hA, d.SA); if (rc) return rc; }
+        if (m > 0) { c_int rc = upload_tile_stream(e, hT, d.ST); if (rc) return rc; }
+        CU_OK(dalloc(e, &d.Pu, (size_t)n + 8));
+        CU_OK(configure_dyn_smem(e.geom.dyn_smem));
+        if (max_coop_blocks_per_sm(e.geom.block, e.geom.dyn_smem) < 1) {
+          fprintf(stderr, "ERROR in osqp_setup: shared-memory slice of %zu bytes does not fit\n", e.geom.dyn_smem);
+          return 13;
+        }
+        d.blocked = 1;
+      } else {
+        e.geom.dyn_smem = 0;
       }
     }
   }
