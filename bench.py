@@ -192,19 +192,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = pkg.load_library(graft.LIB)
-    prof_t = None
-
     def profile(mdl):
-        nonlocal prof_t
-        if prof_t is None:
-            fields = [("device", C.c_longlong), ("grid", C.c_longlong), ("block", C.c_longlong),
-                      ("lanes_A", C.c_longlong), ("lanes_N", C.c_longlong), ("nnz_A", C.c_longlong),
-                      ("nnz_P_full", C.c_longlong), ("launches", C.c_longlong), ("admm_iters", C.c_longlong),
-                      ("pcg_iters", C.c_longlong), ("info_evals", C.c_longlong), ("refreshes", C.c_longlong),
-                      ("kernel_ms", C.c_double), ("polish_ms", C.c_double), ("alg_bytes", C.c_double),
-                      ("spmv_bytes_A", C.c_double), ("spmv_bytes_At", C.c_double), ("spmv_bytes_P", C.c_double)]
-            prof_t = type("Profile", (C.Structure,), {"_fields_": fields})
-        p = prof_t()
+        p = pkg.types.B200Profile()
         assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(p)) == 0
         return p
 

@@ -31,6 +31,12 @@ typedef struct {
   c_float spmv_bytes_A;  /* algorithmic bytes of one A v, A'w, (P+sigma I)v  (12 B/nnz CSR model) */
   c_float spmv_bytes_At;
   c_float spmv_bytes_P;
+  /* last solve: wall time (us) thread block 0 spent per phase class of the admm_kernel launch.
+   * PCG iteration: 0 stream [A;P]u | 1 grid barrier | 2 combine partials -> t, rho.*t, Pu | 3 reduce + barrier |
+   * 4 stream A'(rho.*t) | 5 grid barrier | 6 vector recurrences | 7 reduce + barrier.  ADMM step: 8 x,z,y update,
+   * rhs vector, barriers | 9 stream A' rhs + barrier | 10 rhs/residual + reduce | 11 residual refresh (CSR path) |
+   * 12 update_info (CSR path) | 13 rho update | 14 epilogue | 15 unused */
+  c_float phase_us[16];
 } OSQPB200Profile;
 
 /* Measurement of the last osqp_solve on this workspace. */
@@ -60,6 +66,11 @@ c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int c
  * declines the matrix (padding / capacity), > 2 on a format violation.  Needs no GPU. */
 c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
                                 const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio);
+
+/* Stream micro-benchmark: GB/s of reading `mbytes` MB with the load shape of the tile-stream phase (per lane and
+ * chunk 2 x 16 B + 8 B, `depth` chunks in flight).  pattern 0: one contiguous share per warp; 1: the 16 warps of a
+ * block interleave chunk by chunk; 2: as 1 with values and columns of a chunk in one 1280 B record.  < 0 on error. */
+c_float osqp_b200_membench(c_int mbytes, c_int pattern, c_int depth, c_int reps);
 
 c_int osqp_b200_device_count(void);
 

@@ -17,6 +17,7 @@ namespace osqpb200 {
 constexpr int kMaxBlocks = 1184;      // 148 SMs x 8
 constexpr int kRedSlots = 32;         // scalars reduced per grid barrier
 constexpr int kLogRows = 64;          // verbose table rows buffered per solve
+constexpr int kPhases = 16;           // phase classes timed by block 0 (include/osqp_b200.h OSQPB200Profile.phase_us)
 
 struct CsrDev {
   int rows = 0, cols = 0;
@@ -38,7 +39,8 @@ struct CsrDev {
 //     warp's entries are stored contiguously, row by row.  There is no row pointer: an entry is (fp64 value, u16
 //     word = column local to the group slice); every row segment is padded with zero entries to a multiple of 4 (a
 //     "quad"), and bit 15 of the LAST word of a quad marks the end of a row.  Each lane streams whole quads with two
-//     16 B value loads and one 8 B column load, perfectly coalesced and aligned: 10 B per stored entry.
+//     16 B value loads and one 8 B column load: 10 B per stored entry.  Inside a chunk (32 quads) the values are
+//     interleaved so that each of the two value loads of a warp covers one contiguous 512 B row (whole sectors).
 //   * A lane sums its quad; row sums are formed with a warp-segmented scan over the per-lane flags (carry across
 //     chunks) and written straight to part[group][row].  The owner blocks add the `ngroups` partial vectors in the
 //     element-wise phase that follows the next grid barrier (fixed order -> run-to-run deterministic).
@@ -49,6 +51,7 @@ struct TileStreamDev {
   int rows = 0, cols = 0;        // stacked rows, length of the gathered vector
   int ngroups = 0;
   int pf_chunks = 0;             // chunks (32 quads = 1280 B) a warp prefetches into L2 ahead of its register loads
+  int variant = 0;               // 0: product path; > 0: measurement variants of stream_phase (kernels.cu)
   long long nelem = 0;           // padded stream length in entries (multiple of 4)
   double *val = nullptr;         // [nelem] scaled values (zero on padding)
   unsigned short *cf = nullptr;  // [nelem] local column; bit 15 of every 4th word: row ends with this quad
@@ -56,7 +59,8 @@ struct TileStreamDev {
   int *blk_group = nullptr;      // [grid]
   int *grp_col0 = nullptr;       // [ngroups + 1] column range of each group (multiples of 32)
   int *w_row0 = nullptr;         // [grid * kWarps] first stacked row of warp i
-  int *w_q0 = nullptr;           // [grid * kWarps + 1] quads [w_q0[i], w_q0[i+1]) are the stream of warp i
+  int *w_q0 = nullptr;           // [grid * kWarps + 1] first quad of warp i's stream (a multiple of 32 = one chunk)
+  int *w_qn = nullptr;           // [grid * kWarps] quads in warp i's stream
   double *part = nullptr;        // [ngroups][rows] partial row sums of the last phase
 };
 
@@ -87,6 +91,7 @@ struct DevInfo {
   long long refreshes;          // full residual / z_tilde rebuilds
   double elapsed_s;             // device-side wall time of the loop (globaltimer)
   long long log_rows;
+  double phase_us[kPhases];     // block 0's wall time per phase class (PhaseClock in kernels.cu)
   double log[kLogRows][6];      // iter, obj, pri_res, dua_res, rho, time
 };
 
@@ -189,5 +194,7 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
 int max_coop_blocks_per_sm(int block, size_t dyn_smem);
 cudaError_t configure_dyn_smem(size_t dyn_smem);
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
+cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int depth, int grid, double *sink,
+                            cudaStream_t st);
 
 }  // namespace osqpb200

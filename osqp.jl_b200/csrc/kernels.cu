@@ -53,11 +53,30 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-__device__ __forceinline__ unsigned ld_stream(const unsigned short *p) {
-  unsigned short v;
-  asm("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
-  return v;
-}
+// Block 0 / thread 0 attributes its wall time to phase classes (shared-memory accumulators, copied to DevInfo at exit).
+//  0 stream [A;P]  1 barrier  2 combine t,Pu (+delta)  3 reduce+barrier  4 stream A'  5 barrier  6 vector update
+//  7 reduce+barrier | 8 z,y,x update + rhs vector + barrier  9 stream A' rhs + barrier  10 rhs/residual + reduce
+//  11 residual refresh (CSR path)  12 update_info (CSR path)  13 rho update  14 other
+struct PhaseClock {
+  double *acc;
+  unsigned long long t;
+  bool on;
+  __device__ __forceinline__ void start(double *a) {
+    acc = a;
+    on = (blockIdx.x == 0 && threadIdx.x == 0);
+    if (on) {
+      for (int k = 0; k < kPhases; k++) acc[k] = 0.0;
+      t = globaltimer_ns();
+    }
+  }
+  __device__ __forceinline__ void tick(int k) {
+    if (on) {
+      const unsigned long long now = globaltimer_ns();
+      acc[k] += (double)(now - t) * 1e-3;
+      t = now;
+    }
+  }
+};
 
 // ------------------------------------------------------------------ tile streams (engine.cuh TileStreamDev)
 // Shared-memory staging of the gathered vector slice: one elected thread arms an mbarrier with the byte count and
@@ -67,6 +86,7 @@ struct Slice {
   unsigned xs;       // shared-space address of the staged slice
   unsigned mbar;     // shared-space address of its mbarrier
   unsigned parity;
+  unsigned long long *probe;  // spmv_stream_kernel only: globaltimer when the slice has landed (else nullptr)
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -76,6 +96,7 @@ __device__ __forceinline__ void slice_init(Slice &S, const DevPtrs &d) {
   S.xs = smem_u32(dyn_smem);
   S.mbar = S.xs + 8u * (unsigned)d.smem_x_elems;
   S.parity = 0;
+  S.probe = nullptr;
   if (d.blocked) {
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(S.mbar));
@@ -117,12 +138,15 @@ struct QuadSlot {
 };
 
 // pv / pc: this lane's byte addresses inside the value / column streams
+// pv / pc: this lane's byte addresses inside the value / column streams.  Explicit L2 eviction priorities
+// (createpolicy + .L2::cache_hint: evict_last on some streams, evict_first on the others) were measured on B200 and
+// made every phase slower (profiles/r1_notes.md), so the loads carry no hint.
 __device__ __forceinline__ void quad_load(QuadSlot &q, const char *pv, const char *pc, bool active) {
   q.v0 = q.v1 = q.v2 = q.v3 = 0.0;
   q.c01 = q.c23 = 0u;
   if (active) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(q.v0), "=d"(q.v1) : "l"(pv));
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(q.v2), "=d"(q.v3) : "l"(pv + 16));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(q.v2), "=d"(q.v3) : "l"(pv + 512));
     asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(q.c01), "=r"(q.c23) : "l"(pc));
   }
 }
@@ -130,10 +154,10 @@ __device__ __forceinline__ void quad_load(QuadSlot &q, const char *pv, const cha
 // Warm L2 with the head of this warp's stream of T; call before the grid barrier that precedes the phase.
 __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
   const int lane = threadIdx.x & 31, wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
-  const int q0 = __ldg(T.w_q0 + wid), total = __ldg(T.w_q0 + wid + 1) - q0;
+  const int q0 = __ldg(T.w_q0 + wid), total = __ldg(T.w_qn + wid);
   if (lane < T.pf_chunks && lane * 32 < total) {
     const unsigned quads = (unsigned)min(32, total - lane * 32);
-    l2_prefetch(T.val + 4ll * (q0 + lane * 32), quads * 32u);
+    l2_prefetch(T.val + 4ll * (q0 + lane * 32), 1024u);
     l2_prefetch(T.cf + 4ll * (q0 + lane * 32), quads * 8u);
   }
 }
@@ -141,7 +165,10 @@ __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
 // One phase of  part[group][row] = sum over the block's column group of M[row, :] vec  for the rows of every warp.
 // Must be entered by all threads of the block after a grid barrier (the previous users of the slice are done and
 // `vec` is complete and visible).
-__device__ __noinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
+// kD: chunks in flight per lane.  kExp != 0: measurement variants (profiles/probe_spmv.py), results are wrong:
+// 1 = no segmented scan, 2 = no gather from the staged slice, 3 = neither and no stores (loads + FMAs only).
+template <int kD, int kExp>
+__device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int grp = __ldg(T.blk_group + b);
   const unsigned parity = S.parity;
@@ -163,14 +190,14 @@ __device__ __noinline__ void stream_phase(Slice &S, const TileStreamDev &T, cons
     }
   }
   const int wid = b * kWarps + warp;
-  const int q0 = __ldg(T.w_q0 + wid), L = __ldg(T.w_q0 + wid + 1) - q0;  // quads of this warp
+  const int q0 = __ldg(T.w_q0 + wid), L = __ldg(T.w_qn + wid);  // first quad (chunk aligned), quads of this warp
   if (L <= 0) {
     // warp 0 still drains the mbarrier it armed so that the next phase never re-arms a pending one
     if (warp == 0) mbar_wait(S.mbar, parity);
     return;
   }
   double *__restrict__ out = T.part + (size_t)grp * T.rows + __ldg(T.w_row0 + wid);
-  const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * (q0 + lane);
+  const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * q0 + 16 * lane;
   const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
   const char *pf_v = reinterpret_cast<const char *>(T.val) + 32ll * q0;
   const char *pf_c = reinterpret_cast<const char *>(T.cf) + 8ll * q0;
@@ -191,15 +218,20 @@ __device__ __noinline__ void stream_phase(Slice &S, const TileStreamDev &T, cons
       const int pq = (issued + pf) * 32;
       if (pq < L) {
         const unsigned quads = (unsigned)min(128, L - pq);
-        l2_prefetch(pf_v + 32ll * pq, quads * 32u);
+        l2_prefetch(pf_v + 32ll * pq, ((quads + 31u) & ~31u) * 32u);
         l2_prefetch(pf_c + 8ll * pq, quads * 8u);
       }
     }
     issued++;
   };
   auto consume = [&](const QuadSlot &q) {
-    const double x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
-    const double x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    double x0, x1, x2, x3;
+    if (kExp >= 2) {
+      x0 = x1 = x2 = x3 = 1.0;
+    } else {
+      x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+      x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    }
     double inc = q.v0 * x0;
     inc = fma(q.v1, x1, inc);
     inc = fma(q.v2, x2, inc);
@@ -208,45 +240,63 @@ __device__ __noinline__ void stream_phase(Slice &S, const TileStreamDev &T, cons
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     const unsigned below = bal & lt;
     const int h = 32 - __clz(below);  // first lane of the row this lane's quad belongs to (0 if none ended below)
+    if (kExp != 1 && kExp != 3) {
 #pragma unroll
-    for (int dlt = 1; dlt < 32; dlt <<= 1) {
-      const double t = __shfl_up_sync(0xffffffffu, inc, dlt);
-      if (lane - dlt >= h) inc += t;
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, inc, dlt);
+        if (lane - dlt >= h) inc += t;
+      }
     }
     if (below == 0u) inc += carry;  // the row started in an earlier chunk
-    if (flag) out[rdone + __popc(below)] = inc;
+    if (kExp == 3) {
+      if (inc == 1.2345e300) out[0] = inc;
+    } else if (flag) out[rdone + __popc(below)] = inc;
     const double last = __shfl_sync(0xffffffffu, inc, 31);
     carry = (bal >> 31) ? 0.0 : last;
     rdone += __popc(bal);
   };
 
-  QuadSlot slot[kDepth];
+  QuadSlot slot[kD];
 #pragma unroll
-  for (int k = 0; k < kDepth; k++) issue(slot[k]);
+  for (int k = 0; k < kD; k++) issue(slot[k]);
   mbar_wait(S.mbar, parity);  // the slice has landed (the first matrix loads are already in flight)
+  if (S.probe != nullptr && tid == 0) S.probe[6] = globaltimer_ns();
   const int nchunks = (L + 31) >> 5;
-  for (int base = 0; base < nchunks; base += kDepth) {
+  for (int base = 0; base < nchunks; base += kD) {
 #pragma unroll
-    for (int k = 0; k < kDepth; k++) {
-      if (base + k < nchunks) consume(slot[k]);
+    for (int k = 0; k < kD; k++) {
+      consume(slot[k]);  // slots past the end hold zeros without flags: a no-op that keeps carry and rdone
       issue(slot[k]);
     }
   }
 }
 
+__device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
+  switch (T.variant) {
+    case 1: stream_phase_impl<kDepth, 1>(S, T, vec); break;
+    case 2: stream_phase_impl<kDepth, 2>(S, T, vec); break;
+    case 3: stream_phase_impl<kDepth, 3>(S, T, vec); break;
+    case 4: stream_phase_impl<2, 0>(S, T, vec); break;
+    default: stream_phase_impl<kDepth, 0>(S, T, vec); break;
+  }
+}
+
 // ------------------------------------------------------------------ grid barrier + reductions
+// One monotonically increasing arrival counter (reset to 0 by the host before every cooperative launch): barrier
+// k is passed once the counter reaches k * nblocks.  Per block one thread arrives with a release reduction (no
+// return value, no reset, no second atomic) and spins on an acquire load; critical path = one L2 round trip + one
+// poll.  The block's other threads are ordered through the two __syncthreads().
 struct Grid {
-  unsigned *count, *gen;
-  unsigned nblocks, local_gen;
+  unsigned *count;
+  unsigned nblocks, target;
   int bank;
   double *red;
 };
 
 __device__ __forceinline__ void grid_init(Grid &g, const DevPtrs &d) {
   g.count = d.bar;
-  g.gen = d.bar + 1;
   g.nblocks = gridDim.x;
-  g.local_gen = ld_acquire(g.gen);  // nobody can advance it before every block has arrived once
+  g.target = 0u;
   g.bank = 0;
   g.red = d.red;
 }
@@ -254,20 +304,13 @@ __device__ __forceinline__ void grid_init(Grid &g, const DevPtrs &d) {
 __device__ __forceinline__ void grid_barrier(Grid &g) {
   __syncthreads();
   if (g.nblocks > 1) {
+    g.target += g.nblocks;
     if (threadIdx.x == 0) {
-      __threadfence();
-      unsigned arrived = atomicAdd(g.count, 1u);
-      if (arrived == g.nblocks - 1) {
-        atomicExch(g.count, 0u);
-        __threadfence();
-        atomicAdd(g.gen, 1u);
-      } else {
-        while (ld_acquire(g.gen) == g.local_gen) {
-        }
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(g.count) : "memory");
+      while ((int)(ld_acquire(g.count) - g.target) < 0) {
       }
-      __threadfence();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
     }
-    g.local_gen++;
     __syncthreads();
   }
 }
@@ -383,7 +426,8 @@ struct PcgVecs {
   double *r, *uu, *p, *s, *w, *t, *tr, *Ap;
 };
 
-__device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, const DevPtrs &d, const PcgVecs &v, const double *rho_vec,
+__device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const DevPtrs &d, const PcgVecs &v,
+                                    const double *rho_vec,
                                     const double *Minv, double sigma, double *xvec, double *zvec, double gamma,
                                     double rn, double thresh, int max_it, int m0, int m1, int n0, int n1) {
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -464,7 +508,9 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, const DevPtrs &d, cons
         zvec[i] += alpha * api;
       }
     }
+    pc.tick(6);
     reduce_and_barrier<2>(g, sm, red2, 0x2u);
+    pc.tick(7);
     gamma_old = gamma;
     gamma = red2[0];
     rn = red2[1];
@@ -486,8 +532,8 @@ __device__ __forceinline__ double part_sum(const TileStreamDev &T, int row) {
 //   phase C : owners: t = sum of partials, tr = rho .* t, Pu; delta = uu'P uu + sigma |uu|^2 + t'tr | reduce + barrier
 //   phase B : A' tr      -> partial row sums per column group                      | barrier
 //   phase V : owners: w = Pu + sigma uu + sum of partials, vector recurrences      | reduce + barrier
-__device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, const DevPtrs &d, const PcgVecs &v,
-                                           const double *rho_vec, const double *Minv, double sigma, double *xvec,
+__device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, PhaseClock &pc, const DevPtrs &d,
+                                           const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma, double *xvec,
                                            double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
                                            int m1, int n0, int n1) {
   const int tid = threadIdx.x, nth = blockDim.x;
@@ -498,67 +544,89 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, const
     // ---- phase A
     stream_phase(S, d.SA, v.uu);
     if (m > 0) stream_prefetch_head(d.ST);
+    pc.tick(0);
     grid_barrier(g);
-    // ---- phase C
+    pc.tick(1);
+    // ---- phase C (beta only needs the gammas of the previous reductions)
+    const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     double red1[1] = {0.0};
-    for (int i = m0 + tid; i < m1; i += nth) {
-      const double ti = part_sum(d.SA, i);
-      const double tri = rho_vec[i] * ti;
-      v.t[i] = ti;
-      v.tr[i] = tri;
-      red1[0] += ti * tri;
+    {
+      // the blocks own ~2 rows of A and ~1 row of P per thread: issue every load of the first round before the
+      // first dependent store so the phase costs one L2 round trip, not one per loop
+      const int j0 = n0 + tid;
+      double pu0 = 0.0, uj0 = 0.0;
+      if (j0 < n1) {
+        pu0 = part_sum(d.SA, m + j0);
+        uj0 = v.uu[j0];
+      }
+      for (int i = m0 + tid; i < m1; i += nth) {
+        const double ti = part_sum(d.SA, i);
+        const double tri = rho_vec[i] * ti;
+        if (zvec != nullptr) v.Ap[i] = (it == 0) ? ti : ti + beta * v.Ap[i];  // A p, for the z = A x recurrence
+        v.tr[i] = tri;
+        red1[0] += ti * tri;
+      }
+      if (j0 < n1) {
+        d.Pu[j0] = pu0;
+        red1[0] += uj0 * (pu0 + sigma * uj0);
+      }
+      for (int j = j0 + nth; j < n1; j += nth) {
+        const double pu = part_sum(d.SA, m + j);
+        const double uj = v.uu[j];
+        d.Pu[j] = pu;
+        red1[0] += uj * (pu + sigma * uj);
+      }
     }
-    for (int j = n0 + tid; j < n1; j += nth) {
-      const double pu = part_sum(d.SA, m + j);
-      const double uj = v.uu[j];
-      d.Pu[j] = pu;
-      red1[0] += uj * (pu + sigma * uj);
-    }
+    pc.tick(2);
     if (m > 0) {
       reduce_and_barrier<1>(g, sm, red1, 0u);
+      pc.tick(3);
       // ---- phase B
       stream_phase(S, d.ST, v.tr);
       stream_prefetch_head(d.SA);
+      pc.tick(4);
       grid_barrier(g);
+      pc.tick(5);
     } else {
       reduce_and_barrier<1>(g, sm, red1, 0u);
+      pc.tick(3);
     }
     const double delta = red1[0];
-    double beta, alpha;
-    if (it == 0) {
-      beta = 0.0;
-      alpha = gamma / delta;
-    } else {
-      beta = gamma / gamma_old;
-      alpha = gamma / (delta - beta * gamma / a_old);
-    }
+    const double alpha = (it == 0) ? gamma / delta : gamma / (delta - beta * gamma / a_old);
     if (!(alpha > 0.0) || !isfinite(alpha)) break;  // breakdown: p'Kp <= 0 or exact convergence
     // ---- phase V
     double red2[2] = {0.0, 0.0};
-    for (int j = n0 + tid; j < n1; j += nth) {
-      const double uj = v.uu[j];
-      double wj = d.Pu[j] + sigma * uj;
-      if (m > 0) wj += part_sum(d.ST, j);
-      const double pj = (it == 0) ? uj : uj + beta * v.p[j];
-      const double sj = (it == 0) ? wj : wj + beta * v.s[j];
-      v.p[j] = pj;
-      v.s[j] = sj;
-      xvec[j] += alpha * pj;
-      const double rj = v.r[j] - alpha * sj;
-      v.r[j] = rj;
-      const double un = Minv[j] * rj;
-      v.uu[j] = un;
-      red2[0] += rj * un;
-      red2[1] = fmax(red2[1], fabs(rj));
-    }
-    if (zvec != nullptr) {
-      for (int i = m0 + tid; i < m1; i += nth) {
-        const double api = (it == 0) ? v.t[i] : v.t[i] + beta * v.Ap[i];
-        v.Ap[i] = api;
-        zvec[i] += alpha * api;
+    {
+      const int i0 = m0 + tid;  // first z update of this thread: loads issued ahead of the n loop's stores
+      double ap0 = 0.0, z0 = 0.0;
+      if (zvec != nullptr && i0 < m1) {
+        ap0 = v.Ap[i0];
+        z0 = zvec[i0];
+      }
+      for (int j = n0 + tid; j < n1; j += nth) {
+        const double uj = v.uu[j];
+        double wj = d.Pu[j] + sigma * uj;
+        if (m > 0) wj += part_sum(d.ST, j);
+        const double pj = (it == 0) ? uj : uj + beta * v.p[j];
+        const double sj = (it == 0) ? wj : wj + beta * v.s[j];
+        v.p[j] = pj;
+        v.s[j] = sj;
+        xvec[j] += alpha * pj;
+        const double rj = v.r[j] - alpha * sj;
+        v.r[j] = rj;
+        const double un = Minv[j] * rj;
+        v.uu[j] = un;
+        red2[0] += rj * un;
+        red2[1] = fmax(red2[1], fabs(rj));
+      }
+      if (zvec != nullptr) {
+        if (i0 < m1) zvec[i0] = z0 + alpha * ap0;
+        for (int i = i0 + nth; i < m1; i += nth) zvec[i] += alpha * v.Ap[i];
       }
     }
+    pc.tick(6);
     reduce_and_barrier<2>(g, sm, red2, 0x2u);
+    pc.tick(7);
     gamma_old = gamma;
     gamma = red2[0];
     rn = red2[1];
@@ -722,6 +790,9 @@ __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho
 // ------------------------------------------------------------------ the ADMM kernel
 __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, const SolveCfg c) {
   __shared__ RedSmem sm;
+  __shared__ double phase_acc[kPhases];
+  PhaseClock pc;
+  pc.start(phase_acc);
   Grid g;
   grid_init(g, d);
   Slice SG;
@@ -750,12 +821,14 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   S.pri_res = S.dua_res = S.obj_val = 0.0;
   long long status = ST_UNSOLVED, info_iter = 0, cg_total = 0, cg_solves = 0, checks = 0, log_rows = 0, refreshes = 0;
   double rho_est = rho, elapsed = 0.0;
-  bool can_check = false, can_print = false;
+  bool can_check = false, can_print = false, wv_valid = false;
   long long it;
   for (it = 1; it <= c.max_iter; it++) {
-    // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde)
-    if (d.blocked && !refresh && d.m > 0) stream_prefetch_head(d.ST);
+    // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde).  In steady state wv was already written by
+    //         the Z phase of the previous iteration and its reduce + barrier made it visible: nothing to do here.
+    if (refresh || !wv_valid) {
     for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
+    wv_valid = true;
     if (refresh && d.m > 0) {
       for (int base = m0; base < m1; base += ngrpA) {
         const int row = base + grpA;
@@ -772,6 +845,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       }
     }
     grid_barrier(g);
+    pc.tick(refresh ? 11 : 8);
+    }
     // ---- P2: b = sigma x - q + A' wv ; r = b - K x_tilde (refresh) or r += b - b_old
     double red3[3] = {0.0, 0.0, 0.0};
     if (d.blocked && !refresh) {
@@ -780,6 +855,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
         stream_phase(SG, d.ST, d.wv);
         stream_prefetch_head(d.SA);
         grid_barrier(g);
+        pc.tick(9);
       }
       for (int j = n0 + tid; j < n1; j += nth) {
         const double acc = (d.m > 0) ? part_sum(d.ST, j) : 0.0;
@@ -828,15 +904,16 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       }
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
+    pc.tick(refresh ? 11 : 10);
     refreshes += refresh;
     refresh = 0;
     {
       // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
       // (r0 measures how far the system moved since the last solve), floored at roundoff level
       const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
-      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
                                                  red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
-                                : pcg_run(g, sm, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
+                                : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
                                           thresh, c.pcg_max_iter, m0, m1, n0, n1);
       cg_total += ncg;
       cg_solves++;
@@ -849,8 +926,10 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       const double zh = c.alpha * zti + (1.0 - c.alpha) * zi;
       const double zn = fmin(fmax(zh + rinv * yi, li), ui);
       double dyi = ri * (zh - zn);
-      d.y[i] = yi + dyi;
+      const double yn = yi + dyi;
+      d.y[i] = yn;
       d.z[i] = zn;
+      d.wv[i] = ri * zn - yn;  // rhs vector of the next step (P1)
       if (ui > kInfty * kMinScaling) {
         if (li < -kInfty * kMinScaling) dyi = 0.0;
         else dyi = fmin(dyi, 0.0);
@@ -865,12 +944,14 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       d.dx[j] = xn - xj;
       d.x[j] = xn;
     }
+    if (d.blocked && d.m > 0) stream_prefetch_head(d.ST);
     {
       double redt[1] = {0.0};
       if (b == 0 && tid == 0) redt[0] = (double)(globaltimer_ns() - t_start) * 1e-9;
       reduce_and_barrier<1>(g, sm, redt, 0x1u);
       elapsed = redt[0];
     }
+    pc.tick(8);
     if (c.time_limit_s > -1e29 && elapsed >= c.time_limit_s) {
       status = ST_TIME_LIMIT;
       can_check = false;
@@ -881,6 +962,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     can_print = c.verbose && ((it % kPrintInterval == 0) || it == 1);
     if (can_check || can_print) {
       compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      pc.tick(12);
       info_iter = it;
       checks++;
       if (can_print && b == 0 && tid == 0 && log_rows < kLogRows) {
@@ -917,6 +999,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
         }
         grid_barrier(g);
         precond_rows(d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        pc.tick(13);
         refresh = 1;  // K changed: the residual recurrence is void
       }
     }
@@ -984,6 +1067,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     I->refreshes = refreshes;
     I->elapsed_s = (double)(globaltimer_ns() - t_start) * 1e-9;
     I->log_rows = log_rows;
+    pc.tick(14);
+    for (int k = 0; k < kPhases; k++) I->phase_us[k] = phase_acc[k];
     d.state->rho = rho;
     d.state->rho_updates = rho_updates;
     d.state->adaptive_interval = interval;
@@ -1067,6 +1152,9 @@ __global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const DevPtrs d, 
 __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, const PolishCfg c, const SolveCfg sc,
                                                          PolishOut *out) {
   __shared__ RedSmem sm;
+  __shared__ double phase_acc[kPhases];
+  PhaseClock pc;
+  pc.start(phase_acc);
   Grid g;
   grid_init(g, d);
   Slice SG;
@@ -1143,9 +1231,9 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, co
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
-    cg_total += d.blocked ? pcg_run_stream(g, sm, SG, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
+    cg_total += d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
                                            red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
-                          : pcg_run(g, sm, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1],
+                          : pcg_run(g, sm, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1],
                                     thresh, c.pcg_max_iter, m0, m1, n0, n1);
     // multiplier step on active rows: y += penalty (A x - b)
     for (int i = m0 + tid; i < m1; i += nth)
@@ -1260,6 +1348,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs 
   stream_prefetch_head(T);
   grid_barrier(g);
   if (tid == 0) probe[1] = globaltimer_ns();
+  SG.probe = probe;
   stream_phase(SG, T, in);
   if ((tid & 31) == 0) {
     const unsigned long long t = globaltimer_ns();
@@ -1277,6 +1366,48 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs 
   } else {
     for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.SA, d.m + j) + sigma * in[j];
   }
+}
+
+// ------------------------------------------------------------------ stream micro-benchmark (profiles/membench.py)
+// Reads `bytes` of `buf` with the access shape of stream_phase (per lane and chunk: 2 x 16 B + 8 B loads, kD chunks in
+// flight) and nothing else, so the memory system's ceiling for that shape can be separated from the reduction code.
+//   pattern 0: every warp walks its own contiguous 1/(grid*16) share            (the layout of engine v3)
+//   pattern 1: the 16 warps of a block interleave chunk by chunk in one share   (block-contiguous windows)
+//   pattern 2: as 1, and a chunk is one contiguous 1280 B record (values then columns)
+template <int kD>
+__global__ void __launch_bounds__(kThreads, 1) membench_kernel(const char *buf, long long bytes, int pattern,
+                                                               double *sink) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long nwarps = (long long)gridDim.x * kWarps;
+  const long long chunks_total = bytes / 1280;
+  const long long per_warp = chunks_total / nwarps;
+  const char *vbase = buf, *cbase = buf + chunks_total * 1024;
+  double acc = 0.0;
+  unsigned cacc = 0u;
+  QuadSlot slot[kD];
+  long long issued = 0;
+  auto issue = [&](QuadSlot &q) {
+    if (issued < per_warp) {
+      long long c;  // global chunk index
+      if (pattern == 0) c = ((long long)blockIdx.x * kWarps + warp) * per_warp + issued;
+      else c = (long long)blockIdx.x * kWarps * per_warp + issued * kWarps + warp;
+      const char *pv = (pattern == 2) ? buf + c * 1280 + lane * 16 : vbase + c * 1024 + lane * 16;
+      const char *pc = (pattern == 2) ? buf + c * 1280 + 1024 + lane * 8 : cbase + c * 256 + lane * 8;
+      quad_load(q, pv, pc, true);
+    }
+    issued++;
+  };
+#pragma unroll
+  for (int k = 0; k < kD; k++) issue(slot[k]);
+  for (long long base = 0; base < per_warp; base += kD) {
+#pragma unroll
+    for (int k = 0; k < kD; k++) {
+      acc += slot[k].v0 + slot[k].v1 + slot[k].v2 + slot[k].v3;
+      cacc ^= slot[k].c01 ^ slot[k].c23;
+      issue(slot[k]);
+    }
+  }
+  if (acc == 1.2345 && cacc == 77u) sink[0] = acc;  // keep the loads alive
 }
 
 // ------------------------------------------------------------------ setup kernels (row a2, a3): simple grid-stride
@@ -1509,7 +1640,9 @@ inline int ew_grid(long long work) {
 }
 
 template <typename... Args>
-cudaError_t coop_launch(void (*kernel)(Args...), LaunchGeom g, cudaStream_t st, Args... args) {
+cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cudaStream_t st, Args... args) {
+  cudaError_t e = cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st);  // grid barrier arrival counter
+  if (e != cudaSuccess) return e;
   void *params[] = {(void *)&args...};
   return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, g.dyn_smem, st);
 }
@@ -1554,7 +1687,7 @@ cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st) {
 
 cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st) {
   g.dyn_smem = 0;
-  return coop_launch(pd_probe_kernel, g, st, d, sigma, max_it);
+  return coop_launch(pd_probe_kernel, d.bar, g, st, d, sigma, max_it);
 }
 
 cudaError_t launch_warm_start(const DevPtrs &d, const double *x_in, const double *y_in, int scaling, cudaStream_t st) {
@@ -1575,7 +1708,7 @@ cudaError_t launch_scatter_values(double *dst, const double *vals, const long lo
 }
 
 cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
-  return coop_launch(admm_kernel, g, st, d, cfg);
+  return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
 }
 
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
@@ -1584,7 +1717,17 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
     spmv_kernel<<<g.grid, g.block, 0, st>>>(d, which % 10, in, out, sigma);
     return cudaGetLastError();
   }
-  return coop_launch(spmv_stream_kernel, g, st, d, which, in, out, sigma);
+  return coop_launch(spmv_stream_kernel, d.bar, g, st, d, which, in, out, sigma);
+}
+
+cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int depth, int grid, double *sink,
+                            cudaStream_t st) {
+  const char *b = reinterpret_cast<const char *>(buf);
+  if (depth <= 2) membench_kernel<2><<<grid, kThreads, 0, st>>>(b, bytes, pattern, sink);
+  else if (depth <= 4) membench_kernel<4><<<grid, kThreads, 0, st>>>(b, bytes, pattern, sink);
+  else if (depth <= 6) membench_kernel<6><<<grid, kThreads, 0, st>>>(b, bytes, pattern, sink);
+  else membench_kernel<8><<<grid, kThreads, 0, st>>>(b, bytes, pattern, sink);
+  return cudaGetLastError();
 }
 
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
@@ -1610,7 +1753,7 @@ cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st) {
 
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                           cudaStream_t st) {
-  return coop_launch(polish_kernel, g, st, d, cfg, sc, out);
+  return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
 }
 
 }  // namespace osqpb200

@@ -231,11 +231,18 @@ struct CsrRef {
   const std::vector<int> *rowptr, *col;
   int rows;
 };
+// Values are stored chunk-interleaved: entry t of quad (lane) l of a chunk sits at (t / 2) * 64 + 2 * l + t % 2, so a
+// warp reads a chunk's values as two contiguous 512 B rows (16 B per lane each); the column words stay in entry order.
+inline int stream_val_pos(int p) {
+  const int chunk = p >> 7, l = (p >> 2) & 31, t = p & 3;
+  return (chunk << 7) + ((t >> 1) << 6) + 2 * l + (t & 1);
+}
+
 struct TileStreamHost {
   int rows = 0, cols = 0, ngroups = 0;
   long long nelem = 0, nnz = 0;
   std::vector<unsigned short> cf;
-  std::vector<int> from_csr, blk_group, grp_col0, w_row0, w_q0;
+  std::vector<int> from_csr, blk_group, grp_col0, w_row0, w_q0, w_qn;
   int max_slice = 0;
 };
 
@@ -317,8 +324,10 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
     for (int bb = 0; bb < nblk[g]; bb++) T.blk_group[b0 + bb] = g;
     b0 += nblk[g];
   }
-  // positions: warp by warp, row by row; every row segment is a whole number of quads
+  // positions: warp by warp, row by row; every row segment is a whole number of quads and every warp's stream
+  // starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
   std::vector<int> seg_start((size_t)rows * ngroups, 0);
+  T.w_qn.assign((size_t)grid * kWarps, 0);
   long long pos = 0;
   for (int wid = 0; wid < grid * kWarps; wid++) {
     const int g = T.blk_group[wid / kWarps];
@@ -328,8 +337,11 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       seg_start[si] = (int)pos;
       pos += 4 * quads_of(cnt[si]);
     }
+    T.w_qn[wid] = (int)(pos / 4) - T.w_q0[wid];
+    pos = (pos + 127) & ~127LL;
   }
   T.w_q0[(size_t)grid * kWarps] = (int)(pos / 4);
+  if (pos > 2147483000LL) return false;
   T.nelem = pos;
   T.cf.assign((size_t)pos + 8, 0);
   T.from_csr.resize(nnz);
@@ -343,7 +355,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
           const int c = (*M.col)[k], g = c / Wg;
           const int p = cursor[(size_t)(r0 + r) * ngroups + g]++;
           T.cf[p] = (unsigned short)(c - g * Wg);
-          T.from_csr[k0 + k] = p;
+          T.from_csr[k0 + k] = stream_val_pos(p);
         }
       r0 += M.rows;
       k0 += (*M.rowptr)[M.rows];
@@ -354,6 +366,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
 }
 
 c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
+  t.variant = env_int("OSQP_B200_STREAM_VARIANT", 0);
   t.rows = h.rows; t.cols = h.cols; t.ngroups = h.ngroups; t.nelem = h.nelem;
   t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 8))) & ~3;
   CU_OK(dalloc(e, &t.val, (size_t)h.nelem + 8));
@@ -364,6 +377,7 @@ c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
   CU_OK(dalloc(e, &dst, (vec).size()));                                                                      \
   CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
   UP(t.blk_group, h.blk_group); UP(t.grp_col0, h.grp_col0); UP(t.w_row0, h.w_row0); UP(t.w_q0, h.w_q0);
+  UP(t.w_qn, h.w_qn);
 #undef UP
   CU_OK(cudaMemcpyAsync(t.cf, h.cf.data(), (size_t)h.nelem * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
   if (h.nnz > 0)
@@ -498,15 +512,20 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
   TileStreamHost T;
   std::vector<CsrRef> mats{CsrRef{&rp, &ci, (int)rows}};
   if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, T)) return 2;
-  if (padding_ratio) *padding_ratio = T.nnz ? (double)T.nelem / (double)T.nnz : 1.0;
+  if (padding_ratio) {  // entries actually streamed (quad padding, zero quads) per non-zero
+    long long quads = 0;
+    for (int q : T.w_qn) quads += q;
+    *padding_ratio = T.nnz ? 4.0 * (double)quads / (double)T.nnz : 1.0;
+  }
   std::vector<double> sv((size_t)T.nelem + 8, 0.0);
   for (long long k = 0; k < T.nnz; k++) sv[T.from_csr[k]] = val[k];
   std::vector<double> part((size_t)T.ngroups * rows, 0.0);
   std::vector<char> written((size_t)T.ngroups * rows, 0);
   for (int wid = 0; wid < (int)grid * kWarps; wid++) {
     const int grp = T.blk_group[wid / kWarps];
-    const int q0 = T.w_q0[wid], L = T.w_q0[wid + 1] - q0;
+    const int q0 = T.w_q0[wid], L = T.w_qn[wid];
     if (L <= 0) continue;
+    if (q0 % 32 != 0) return 3;
     const double *xs = x + T.grp_col0[grp];
     const int slice = T.grp_col0[grp + 1] - T.grp_col0[grp];
     double *out = part.data() + (size_t)grp * rows + T.w_row0[wid];
@@ -525,8 +544,9 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
             const unsigned w = T.cf[e + t];
             const int lc = (int)(w & 0x7fffu);
             if ((w & 0x8000u) && t != 3) return 4;  // only the last word of a quad may carry the flag
-            if (sv[e + t] != 0.0 && lc >= slice) return 5;
-            acc = (t == 0) ? sv[e] * xs[lc] : std::fma(sv[e + t], xs[lc], acc);
+            const double v = sv[stream_val_pos((int)(e + t))];
+            if (v != 0.0 && lc >= slice) return 5;
+            acc = (t == 0) ? v * xs[lc] : std::fma(v, xs[lc], acc);
           }
           flag = (T.cf[e + 3] & 0x8000u) != 0;
         }
@@ -551,6 +571,41 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
     y_out[r] = a;
   }
   return 0;
+}
+
+// Stream micro-benchmark (kernels.cu membench_kernel): GB/s of reading `mbytes` MB with the load shape of the
+// tile-stream phase.  pattern 0/1/2, depth = chunks in flight per lane.  Standalone: needs no workspace.
+c_float osqp_b200_membench(c_int mbytes, c_int pattern, c_int depth, c_int reps) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return -1.0;
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return -1.0;
+  const int grid = prop.multiProcessorCount;
+  long long bytes = (long long)mbytes * 1000000LL;
+  bytes -= bytes % (1280LL * grid * kWarps);
+  char *buf = nullptr;
+  double *sink = nullptr;
+  if (cudaMalloc(&buf, bytes + 4096) != cudaSuccess) return -1.0;
+  cudaMalloc(&sink, 64);
+  cudaMemset(buf, 0, bytes + 4096);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  launch_membench(buf, bytes, (int)pattern, (int)depth, grid, sink, 0);
+  cudaEventRecord(e0, 0);
+  for (c_int r = 0; r < reps; r++) launch_membench(buf, bytes, (int)pattern, (int)depth, grid, sink, 0);
+  cudaEventRecord(e1, 0);
+  cudaError_t err = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (err != cudaSuccess || ms <= 0.f) return -1.0;
+  return (double)bytes * (double)reps / ((double)ms * 1e-3) / 1e9;
 }
 
 c_int osqp_b200_device_count(void) {
@@ -872,6 +927,7 @@ c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
   e.prof.pcg_iters = I.cg_iters;
   e.prof.info_evals = I.checks;
   e.prof.refreshes = I.refreshes;
+  for (int k = 0; k < kPhases; k++) e.prof.phase_us[k] = I.phase_us[k];
   {
     // algorithmic bytes of this launch (DESIGN.md "bytes model"): matrix streams + dense vector passes
     const double bA = e.prof.spmv_bytes_A, bAt = e.prof.spmv_bytes_At, bP = e.prof.spmv_bytes_P;

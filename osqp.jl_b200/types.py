@@ -166,3 +166,12 @@ class Results:  # src/types.jl:256-272
             self.y = np.empty(m)
             self.prim_inf_cert = np.empty(m)
         return self
+
+
+class B200Profile(C.Structure):
+    """include/osqp_b200.h OSQPB200Profile -- engine extension, not part of the reference ABI."""
+
+    _fields_ = [(k, c_int) for k in ("device", "grid", "block", "lanes_A", "lanes_N", "nnz_A", "nnz_P_full", "launches",
+                                     "admm_iters", "pcg_iters", "info_evals", "refreshes")] + \
+               [(k, c_float) for k in ("kernel_ms", "polish_ms", "alg_bytes", "spmv_bytes_A", "spmv_bytes_At",
+                                       "spmv_bytes_P")] + [("phase_us", c_float * 16)]

@@ -17,9 +17,9 @@ for which, ilen in ((0, bench.N_VARS), (1, bench.N_CONS)):
     eng.osqp_b200_debug_read(mdl.workspace, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), C.c_longlong(buf.size))
     t = buf.reshape(148, 16).astype(np.int64)
     t0 = t[:, 0].min()
-    rel = (t[:, :6] - t0) / 1e3
+    rel = (t[:, :7] - t0) / 1e3
     print("which", which, "event ms/launch", ms.value)
-    print("  probes (us after the earliest block start): start, barrier1, first warp done, last warp done, block done, barrier2")
+    print("  probes (us after the earliest block start): start, barrier1, first warp done, last warp done, block done, barrier2, slice landed")
     print("  mean", np.round(rel.mean(0), 2), "\n  min ", np.round(rel.min(0), 2), "\n  max ", np.round(rel.max(0), 2))
     dur = rel[:, 3] - rel[:, 1]
     order = np.argsort(dur)

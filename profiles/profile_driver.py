@@ -32,9 +32,18 @@ eng = pkg.load_library(graft.LIB)
 prob = bench.make_problem(args.n, args.m, args.density, bench.SEED)
 mdl = pkg.Model(lib=graft.LIB)
 mdl.setup(**prob, **dict(bench.SETTINGS, max_iter=args.max_iter, warm_start=False))
+PHASES = ["stream[A;P]", "barrier", "combine", "reduce+bar", "stream A'", "barrier", "vectors", "reduce+bar",
+          "admm z/y/x+bar", "admm A'rhs+bar", "admm rhs+red", "refresh(CSR)", "info(CSR)", "rho upd", "epilogue", "-"]
 for _ in range(args.solves):
     r = mdl.solve()
     print("solve:", r.info.status, r.info.iter, f"{r.info.solve_time * 1e3:.1f} ms")
+    p = pkg.types.B200Profile()
+    eng.osqp_b200_get_profile(mdl.workspace, C.byref(p))
+    tot = sum(p.phase_us) or 1.0
+    print(f"  kernel {p.kernel_ms:.1f} ms, admm {p.admm_iters}, pcg {p.pcg_iters}, info {p.info_evals}, refresh {p.refreshes};"
+          f" phase total {tot / 1e3:.1f} ms")
+    print("  per PCG it (us):  " + "  ".join(f"{PHASES[k]} {p.phase_us[k] / max(1, p.pcg_iters):.2f}" for k in range(8)))
+    print("  per ADMM it (us): " + "  ".join(f"{PHASES[k]} {p.phase_us[k] / max(1, p.admm_iters):.2f}" for k in range(8, 15)))
 fp = C.POINTER(C.c_double)
 eng.osqp_b200_spmv.restype = C.c_longlong
 rng = np.random.default_rng(1)
