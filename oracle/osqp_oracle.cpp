@@ -12,7 +12,7 @@
 // Parity status: PINNED on the reference's own known-answer tests (test/basic.jl,
 // polishing.jl incl. the Mosek JLD2 fixture, dual_/primal_infeasibility.jl,
 // non_convex.jl, unconstrained.jl, warm_start.jl invariants) -- see
-// tests/test_oracle_pins.py.  UNPINNED at the BASELINE.json sizes (the
+// tests/test_reference_suite.py.  UNPINNED at the BASELINE.json sizes (the
 // reference holds no test larger than 100x500) and against a live libosqp
 // (none exists in this container).
 //

@@ -551,30 +551,33 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     double red1[1] = {0.0};
     {
-      // the blocks own ~2 rows of A and ~1 row of P per thread: issue every load of the first round before the
-      // first dependent store so the phase costs one L2 round trip, not one per loop
-      const int j0 = n0 + tid;
-      double pu0 = 0.0, uj0 = 0.0;
-      if (j0 < n1) {
-        pu0 = part_sum(d.SA, m + j0);
-        uj0 = v.uu[j0];
-      }
-      for (int i = m0 + tid; i < m1; i += nth) {
-        const double ti = part_sum(d.SA, i);
-        const double tri = rho_vec[i] * ti;
-        if (zvec != nullptr) v.Ap[i] = (it == 0) ? ti : ti + beta * v.Ap[i];  // A p, for the z = A x recurrence
-        v.tr[i] = tri;
-        red1[0] += ti * tri;
-      }
-      if (j0 < n1) {
-        d.Pu[j0] = pu0;
-        red1[0] += uj0 * (pu0 + sigma * uj0);
-      }
-      for (int j = j0 + nth; j < n1; j += nth) {
-        const double pu = part_sum(d.SA, m + j);
-        const double uj = v.uu[j];
-        d.Pu[j] = pu;
-        red1[0] += uj * (pu + sigma * uj);
+      // a block owns ~2 rows of A and ~1 row of P per thread: every load of a round (two rows of A, one of P) is
+      // issued before the first dependent store, so the phase costs about one L2 round trip
+      const bool rec = zvec != nullptr && it > 0;
+      int j = n0 + tid;
+      for (int i = m0 + tid; i < m1 || j < n1; i += 2 * nth, j += nth) {
+        const int i2 = i + nth;
+        const bool h1 = i < m1, h2 = i2 < m1, hj = j < n1;
+        double t1 = 0.0, t2 = 0.0, r1 = 0.0, r2 = 0.0, a1 = 0.0, a2 = 0.0, pu = 0.0, uj = 0.0;
+        if (h1) { t1 = part_sum(d.SA, i); r1 = rho_vec[i]; if (rec) a1 = v.Ap[i]; }
+        if (h2) { t2 = part_sum(d.SA, i2); r2 = rho_vec[i2]; if (rec) a2 = v.Ap[i2]; }
+        if (hj) { pu = part_sum(d.SA, m + j); uj = v.uu[j]; }
+        if (h1) {
+          const double tr = r1 * t1;
+          if (zvec != nullptr) v.Ap[i] = t1 + beta * a1;  // A p, for the z = A x recurrence (beta = 0 at it 0)
+          v.tr[i] = tr;
+          red1[0] += t1 * tr;
+        }
+        if (h2) {
+          const double tr = r2 * t2;
+          if (zvec != nullptr) v.Ap[i2] = t2 + beta * a2;
+          v.tr[i2] = tr;
+          red1[0] += t2 * tr;
+        }
+        if (hj) {
+          d.Pu[j] = pu;
+          red1[0] += uj * (pu + sigma * uj);
+        }
       }
     }
     pc.tick(2);
@@ -597,31 +600,38 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     // ---- phase V
     double red2[2] = {0.0, 0.0};
     {
-      const int i0 = m0 + tid;  // first z update of this thread: loads issued ahead of the n loop's stores
-      double ap0 = 0.0, z0 = 0.0;
-      if (zvec != nullptr && i0 < m1) {
-        ap0 = v.Ap[i0];
-        z0 = zvec[i0];
-      }
-      for (int j = n0 + tid; j < n1; j += nth) {
-        const double uj = v.uu[j];
-        double wj = d.Pu[j] + sigma * uj;
-        if (m > 0) wj += part_sum(d.ST, j);
-        const double pj = (it == 0) ? uj : uj + beta * v.p[j];
-        const double sj = (it == 0) ? wj : wj + beta * v.s[j];
-        v.p[j] = pj;
-        v.s[j] = sj;
-        xvec[j] += alpha * pj;
-        const double rj = v.r[j] - alpha * sj;
-        v.r[j] = rj;
-        const double un = Minv[j] * rj;
-        v.uu[j] = un;
-        red2[0] += rj * un;
-        red2[1] = fmax(red2[1], fabs(rj));
-      }
-      if (zvec != nullptr) {
-        if (i0 < m1) zvec[i0] = z0 + alpha * ap0;
-        for (int i = i0 + nth; i < m1; i += nth) zvec[i] += alpha * v.Ap[i];
+      int i = m0 + tid;
+      for (int j = n0 + tid; j < n1 || i < m1; j += nth, i += 2 * nth) {
+        const int i2 = i + nth;
+        const bool hj = j < n1, h1 = zvec != nullptr && i < m1, h2 = zvec != nullptr && i2 < m1;
+        double uj = 0.0, wj = 0.0, pj = 0.0, sj = 0.0, xj = 0.0, rj = 0.0, mj = 0.0;
+        double ap1 = 0.0, z1 = 0.0, ap2 = 0.0, z2 = 0.0;
+        if (hj) {
+          uj = v.uu[j];
+          wj = d.Pu[j] + sigma * uj;
+          if (m > 0) wj += part_sum(d.ST, j);
+          if (it > 0) { pj = v.p[j]; sj = v.s[j]; }
+          xj = xvec[j];
+          rj = v.r[j];
+          mj = Minv[j];
+        }
+        if (h1) { ap1 = v.Ap[i]; z1 = zvec[i]; }
+        if (h2) { ap2 = v.Ap[i2]; z2 = zvec[i2]; }
+        if (hj) {
+          pj = uj + beta * pj;  // beta = 0 at it 0
+          sj = wj + beta * sj;
+          v.p[j] = pj;
+          v.s[j] = sj;
+          xvec[j] = xj + alpha * pj;
+          rj -= alpha * sj;
+          v.r[j] = rj;
+          const double un = mj * rj;
+          v.uu[j] = un;
+          red2[0] += rj * un;
+          red2[1] = fmax(red2[1], fabs(rj));
+        }
+        if (h1) zvec[i] = z1 + alpha * ap1;
+        if (h2) zvec[i2] = z2 + alpha * ap2;
       }
     }
     pc.tick(6);
