@@ -31,6 +31,7 @@ import scipy.sparse as sp
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
+import problems  # noqa: E402
 
 SEED = 20262
 N_VARS, N_CONS, DENSITY = 50_000, 100_000, 1e-3
@@ -39,20 +40,8 @@ SETTINGS = dict(verbose=False, eps_abs=1e-4, eps_rel=1e-4, adaptive_rho_interval
 
 
 def make_problem(n, m, density, seed):
-    """SURVEY.md 8d config C2 construction."""
-    rng = np.random.default_rng(seed)
-    rvs = rng.standard_normal
-    A = sp.random(m, n, density=density, random_state=rng, data_rvs=rvs, format="csc")
-    S = sp.triu(sp.random(n, n, density=density / 2, random_state=rng, data_rvs=rvs, format="csc"), k=1)
-    S = (S + S.T).tocsc()
-    d = np.asarray(abs(S).sum(axis=1)).ravel() + rng.uniform(0.1, 1.0, n)
-    P = (S + sp.diags(d)).tocsc()
-    q = rng.standard_normal(n)
-    x0 = rng.standard_normal(n)
-    Ax0 = A @ x0
-    l = Ax0 - rng.uniform(0, 1, m)
-    u = Ax0 + rng.uniform(0, 1, m)
-    return dict(P=P, q=q, A=A, l=l, u=u)
+    """SURVEY.md 8d config C2 construction (problems.py)."""
+    return problems.random_qp_c2(n, m, density, seed)
 
 
 class ClockSampler:
@@ -148,6 +137,7 @@ def main():
     ap.add_argument("--density", type=float, default=DENSITY)
     ap.add_argument("--cpu-iters", type=int, default=40, help="ADMM iterations per CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch", type=int, default=8192, help="QPs in the batched leg (config 5); 0 disables it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -199,8 +189,10 @@ def main():
 
     prob = make_problem(args.n, args.m, args.density, SEED + rank)
     n, m = args.n, args.m
-    mat_mb = (12.0 * (2 * prob["A"].nnz + prob["P"].nnz)) / 1e6
-    config["l2"] = f"inputs larger than L2: A+A'+P streams = {mat_mb:.0f} MB per K-apply vs 126 MB L2; no flush"
+    mat_mb = (10.6 * (2 * prob["A"].nnz + prob["P"].nnz)) / 1e6  # 10 B per stored entry, 6 % quad padding
+    config["l2"] = (f"inputs larger than L2 (126 MB): {mat_mb:.0f} MB of matrix streams per K-apply plus "
+                    f"{12.0 * (2 * prob['A'].nnz + prob['P'].nnz) / 1e6:.0f} MB of CSR copies read by every "
+                    "termination check; no flush")
     mdl = pkg.Model(lib=graft.LIB)
     t0 = time.perf_counter()
     mdl.setup(**prob, **SETTINGS)
@@ -270,6 +262,48 @@ def main():
             if rc == 0 and ms.value > 0:
                 spmv[name] = {"ms": ms.value, "alg_GBs": nbytes / ms.value / 1e6}
 
+    # ---- batched leg: BASELINE config 5, 8192 MPC QPs (n=30, m=60) sharded over the ranks (strong scaling)
+    batch_line = None
+    if args.batch > 0:
+        lo, hi = pkg.shard_range(args.batch, world, rank)
+        Pp, Ap, Px, Ax, bq, bl, bu = problems.mpc_batch_c5(args.batch, SEED + 5)
+        bm = pkg.BatchModel(lib=graft.LIB)
+        bsettings = dict(verbose=False, eps_abs=1e-4, eps_rel=1e-4, adaptive_rho_interval=25, check_termination=25,
+                         warm_start=False, max_iter=4000)
+        t0 = time.perf_counter()
+        bm.setup(Pp, Ap, Px[lo:hi], Ax[lo:hi], bq[lo:hi], bl[lo:hi], bu[lo:hi], **bsettings)
+        b_setup = time.perf_counter() - t0
+        for _ in range(3):
+            br = bm.solve()
+        barrier()
+        t0 = time.perf_counter()
+        b_iters, b_kern = 0, 0.0
+        for _ in range(args.steps):
+            br = bm.solve()  # host buffers in and out: x*, y*, info of every QP come back each step
+            b_iters += int(br.iter.sum())
+            b_kern += bm.kernel_ms
+        barrier()
+        b_dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        x_all = pkg.batch.gather_sharded(br.x, args.batch, world, rank, device="cuda")  # the only collective
+        barrier()
+        b_gather = time.perf_counter() - t0
+        solved = int(np.sum(br.status_val == 1))
+        bt = torch.tensor([b_dt, b_kern], device="cuda", dtype=torch.float64)
+        bc = torch.tensor([float(b_iters), float(solved)], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(bc, op=dist.ReduceOp.SUM)
+        batch_line = {
+            "workload": f"{args.batch} MPC QPs n=30 m=60, one pattern, cold start, eps=1e-4 (SURVEY 8d C5)",
+            "scaling": "strong", "qps_per_gpu": hi - lo,
+            "qp_iterations_per_sec": float(bc[0]) / float(bt[0]), "solves_per_sec": args.batch * args.steps / float(bt[0]),
+            "kernel_ms_per_step": float(bt[1]) / args.steps, "ms_per_step": 1e3 * float(bt[0]) / args.steps,
+            "mean_iters": float(bc[0]) / (args.batch * args.steps), "solved": int(bc[1]), "setup_s": b_setup,
+            "gather_ms": 1e3 * b_gather, "gathered_rows": int(x_all.shape[0]),
+        }
+        bm.clean()
+
     # ---- aggregate over ranks: sum of iterations, max of time
     if world > 1:
         t = torch.tensor([dt, dt_e2e], device="cuda", dtype=torch.float64)
@@ -316,6 +350,7 @@ def main():
                          "alg_bytes_per_launch": alg_bytes / args.steps, "launch_ms": kern_ms / args.steps,
                          "pcg_iters_per_admm_iter": pcg / max(1.0, float(iters)), "spmv": spmv},
             "cpu_baseline": cpu,
+            "batch": batch_line,
             "clocks": clocks,
             "solve": {"status": status, "admm_iters_per_solve": iters / args.steps, "setup_s": setup_s,
                       "grid": int(p1.grid), "block": int(p1.block), "lanes": [int(p1.lanes_A), int(p1.lanes_N)]},

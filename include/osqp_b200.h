@@ -67,6 +67,36 @@ c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int c
 c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
                                 const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio);
 
+/* ---- batched engine (BASELINE.json config 5; the reference has no batch API -- SURVEY.md 8b "Batch extension") ----
+ * `count` independent QPs that share ONE sparsity pattern (pattern->P upper triangular CSC, pattern->A CSC; the
+ * value arrays of `pattern` are ignored) and differ in their values: Px [count][nnz(P)], Ax [count][nnz(A)],
+ * q [count][n], l/u [count][m], row-major, in the order of the pattern's CSC arrays.  One thread block per QP, all
+ * data in shared memory, exact (dense Cholesky) KKT solve; libosqp 0.6.2 semantics per QP except: no polish, no
+ * time limit, adaptive_rho_interval = 0 means 50 (there is no per-QP wall clock).  n, m <= 256.
+ * A batch lives on one GPU; shard a large batch over GPUs by calling osqp_batch_setup once per device with a
+ * contiguous block of the QPs (osqp.jl_b200/batch.py: shard_range) -- no data is exchanged between shards. */
+typedef struct OSQPB200Batch OSQPB200Batch;
+typedef struct {
+  c_int   iter;
+  c_int   status_val;    /* same codes as OSQPInfo.status_val (src/constants.jl:9-21) */
+  c_float obj_val, pri_res, dua_res, rho_estimate;
+  c_int   rho_updates;
+} OSQPB200BatchInfo;
+
+c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern, const c_float *Px,
+                       const c_float *Ax, const c_float *q, const c_float *l, const c_float *u,
+                       const OSQPSettings *settings);
+/* x_out [count][n], y_out [count][m] (NaN without a solution; for a dual / primal infeasible QP the certificate
+ * delta_x / delta_y is returned in x_out / y_out), info_out [count].  Iterates stay resident for warm starts. */
+c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB200BatchInfo *info_out);
+/* new q / l / u for every QP (NULL: keep); the MPC re-solve pattern of src/modcaches.jl:166-179 */
+c_int osqp_batch_update(OSQPB200Batch *b, const c_float *q, const c_float *l, const c_float *u);
+c_int osqp_batch_warm_start(OSQPB200Batch *b, const c_float *x, const c_float *y);
+/* max_iter, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, alpha, check_termination, warm_start, scaled_termination */
+c_int osqp_batch_update_setting(OSQPB200Batch *b, const char *name, c_float value);
+c_float osqp_batch_last_kernel_ms(const OSQPB200Batch *b);
+c_int osqp_batch_cleanup(OSQPB200Batch *b);
+
 /* Stream micro-benchmark: GB/s of reading `mbytes` MB with the load shape of the tile-stream phase (per lane and
  * chunk 2 x 16 B + 8 B, `depth` chunks in flight).  pattern 0: one contiguous share per warp; 1: the 16 warps of a
  * block interleave chunk by chunk; 2: as 1 with values and columns of a chunk in one 1280 B record.  < 0 on error. */

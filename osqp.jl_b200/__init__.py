@@ -10,3 +10,5 @@ Only what the hot path needs lives here:
 from .constants import *  # noqa: F401,F403
 from .interface import ABI_SYMBOLS, DEFAULT_LIB, Model, ccsc_to_scipy, load_library, ManagedCcsc  # noqa: F401
 from .types import Ccsc, CInfo, Data, Info, Results, Settings, Solution, Workspace  # noqa: F401
+from . import types  # noqa: F401
+from .batch import BatchModel, BatchResults, shard_range  # noqa: F401

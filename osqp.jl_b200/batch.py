@@ -1,0 +1,184 @@
+"""Host side of the batched engine (include/osqp_b200.h ``osqp_batch_*``).
+
+The reference has no batch API (SURVEY.md 8b "Batch extension"); this module is what a Julia helper next to the
+unchanged ``src/*.jl`` would look like: the same marshalling conventions as ``interface.py`` (Int64 0-based CSC,
+upper-triangular P, +-1e30 bound clamp, NaN-fill by status) applied to ``count`` QPs that share one sparsity
+pattern.  A batch lives on one GPU; ``shard_range`` gives the contiguous block of QPs a rank owns when a large batch
+is spread over several GPUs (one process per GPU, problem data scattered once at setup, no collective in the loop).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import types as T
+from .constants import OSQP_INFTY, status_map
+from .interface import ManagedCcsc, load_library
+
+try:
+    import scipy.sparse as sp
+except Exception:  # pragma: no cover
+    sp = None
+
+
+class BatchInfo(C.Structure):
+    """include/osqp_b200.h OSQPB200BatchInfo"""
+
+    _fields_ = [("iter", T.c_int), ("status_val", T.c_int), ("obj_val", T.c_float), ("pri_res", T.c_float),
+                ("dua_res", T.c_float), ("rho_estimate", T.c_float), ("rho_updates", T.c_int)]
+
+
+def shard_range(count, world_size, rank):
+    """Contiguous block [lo, hi) of a batch of `count` QPs owned by `rank` (blocks of ceil(B/G))."""
+    per = -(-count // world_size)
+    lo = min(count, rank * per)
+    return lo, min(count, lo + per)
+
+
+_INFO_DTYPE = np.dtype([("iter", "<i8"), ("status_val", "<i8"), ("obj_val", "<f8"), ("pri_res", "<f8"),
+                        ("dua_res", "<f8"), ("rho_estimate", "<f8"), ("rho_updates", "<i8")])
+assert _INFO_DTYPE.itemsize == C.sizeof(BatchInfo)
+
+
+class BatchResults:
+    def __init__(self, x, y, info):
+        self.x, self.y = x, y
+        a = np.frombuffer(info, dtype=_INFO_DTYPE).copy()
+        self.iter, self.status_val = a["iter"], a["status_val"]
+        self.obj_val, self.pri_res, self.dua_res = a["obj_val"], a["pri_res"], a["dua_res"]
+        self.rho_estimate, self.rho_updates = a["rho_estimate"], a["rho_updates"]
+
+    @property
+    def status(self):
+        return [status_map[int(v)] for v in self.status_val]
+
+
+class BatchModel:
+    """`count` QPs  min 1/2 x'P_k x + q_k'x  s.t.  l_k <= A_k x <= u_k  with one pattern for all P_k and one for all A_k."""
+
+    def __init__(self, lib=None):
+        self.lib = load_library(lib)
+        L = self.lib
+        self._h = C.c_void_p()
+        fp = T.c_float_p
+        L.osqp_batch_setup.restype = T.c_int
+        L.osqp_batch_setup.argtypes = [C.POINTER(C.c_void_p), T.c_int, C.POINTER(T.Data), fp, fp, fp, fp, fp,
+                                       C.POINTER(T.Settings)]
+        L.osqp_batch_solve.restype = T.c_int
+        L.osqp_batch_solve.argtypes = [C.c_void_p, fp, fp, C.POINTER(BatchInfo)]
+        L.osqp_batch_update.restype = T.c_int
+        L.osqp_batch_update.argtypes = [C.c_void_p, fp, fp, fp]
+        L.osqp_batch_warm_start.restype = T.c_int
+        L.osqp_batch_warm_start.argtypes = [C.c_void_p, fp, fp]
+        L.osqp_batch_update_setting.restype = T.c_int
+        L.osqp_batch_update_setting.argtypes = [C.c_void_p, C.c_char_p, T.c_float]
+        L.osqp_batch_last_kernel_ms.restype = T.c_float
+        L.osqp_batch_last_kernel_ms.argtypes = [C.c_void_p]
+        L.osqp_batch_cleanup.restype = T.c_int
+        L.osqp_batch_cleanup.argtypes = [C.c_void_p]
+        self.count = self.n = self.m = 0
+
+    @staticmethod
+    def _f(a):
+        return None if a is None else a.ctypes.data_as(T.c_float_p)
+
+    def setup(self, P_pattern, A_pattern, Px, Ax, q, l, u, **settings):
+        """P_pattern / A_pattern: scipy sparse matrices giving the shared patterns (P is reduced to its upper
+        triangle, src/interface.jl:102-104); Px [count, nnz(triu P)], Ax [count, nnz(A)] follow the CSC order of
+        those patterns; q [count, n]; l, u [count, m]."""
+        Pt = sp.triu(sp.csc_matrix(P_pattern), format="csc")
+        Pt.sort_indices()
+        Ac = sp.csc_matrix(A_pattern)
+        Ac.sort_indices()
+        n, m = Ac.shape[1], Ac.shape[0]
+        Px = np.ascontiguousarray(Px, dtype=np.float64).reshape(-1, Pt.nnz)
+        count = Px.shape[0]
+        Ax = np.ascontiguousarray(Ax, dtype=np.float64).reshape(count, Ac.nnz)
+        q = np.ascontiguousarray(q, dtype=np.float64).reshape(count, n)
+        l = np.clip(np.ascontiguousarray(l, dtype=np.float64).reshape(count, m), -OSQP_INFTY, OSQP_INFTY)
+        u = np.clip(np.ascontiguousarray(u, dtype=np.float64).reshape(count, m), -OSQP_INFTY, OSQP_INFTY)
+        mP, mA = ManagedCcsc(Pt), ManagedCcsc(Ac)
+        cP, cA = mP.ccsc(), mA.ccsc()
+        data = T.Data(n, m, C.pointer(cP), C.pointer(cA), None, None, None)
+        st = T.Settings()
+        self.lib.osqp_set_default_settings(C.byref(st))
+        for k, v in settings.items():
+            if not hasattr(st, k):
+                raise ValueError(f"unknown setting {k}")
+            setattr(st, k, type(getattr(st, k))(v))
+        rc = self.lib.osqp_batch_setup(C.byref(self._h), count, C.byref(data), self._f(Px), self._f(Ax), self._f(q),
+                                       self._f(l), self._f(u), C.byref(st))
+        if rc != 0:
+            self._h = C.c_void_p()
+            raise RuntimeError("Error in OSQP batch setup")
+        self.count, self.n, self.m = count, n, m
+        self.pattern_P, self.pattern_A = Pt, Ac
+        return self
+
+    def solve(self):
+        if not self._h:
+            raise RuntimeError("You are trying to solve an empty batch. Please setup the batch before calling solve().")
+        x = np.empty((self.count, self.n))
+        y = np.empty((self.count, self.m))
+        info = (BatchInfo * self.count)()
+        rc = self.lib.osqp_batch_solve(self._h, self._f(x), self._f(y), info)
+        if rc != 0:
+            raise RuntimeError("Error in OSQP batch solve")
+        return BatchResults(x, y, info)  # rows without a solution are NaN-filled by the engine (certificates aside)
+
+    def update(self, q=None, l=None, u=None):
+        a = []
+        for v, w in ((q, self.n), (l, self.m), (u, self.m)):
+            if v is None:
+                a.append(None)
+                continue
+            v = np.ascontiguousarray(v, dtype=np.float64).reshape(self.count, w)
+            a.append(np.clip(v, -OSQP_INFTY, OSQP_INFTY) if w == self.m and v is not q else v)
+        if self.lib.osqp_batch_update(self._h, self._f(a[0]), self._f(a[1]), self._f(a[2])) != 0:
+            raise RuntimeError("Error updating the batch")
+
+    def warm_start(self, x=None, y=None):
+        x = None if x is None else np.ascontiguousarray(x, dtype=np.float64).reshape(self.count, self.n)
+        y = None if y is None else np.ascontiguousarray(y, dtype=np.float64).reshape(self.count, self.m)
+        if self.lib.osqp_batch_warm_start(self._h, self._f(x), self._f(y)) != 0:
+            raise RuntimeError("Error in batch warm start")
+
+    def update_settings(self, **kw):
+        for k, v in kw.items():
+            if self.lib.osqp_batch_update_setting(self._h, k.encode(), float(v)) != 0:
+                raise ValueError(f"cannot update setting {k}")
+
+    @property
+    def kernel_ms(self):
+        return float(self.lib.osqp_batch_last_kernel_ms(self._h))
+
+    def clean(self):
+        if self._h:
+            self.lib.osqp_batch_cleanup(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.clean()
+        except Exception:
+            pass
+
+
+def gather_sharded(local, count, world_size, rank, device="cpu"):
+    """All-gather per-QP rows computed on contiguous shards (shard_range) into the full [count, ...] array on every
+    rank.  The only collective of the batched path, and it runs AFTER the solves; backend = whatever
+    torch.distributed was initialised with (NCCL over NVLink on GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    local = np.asarray(local)
+    per = -(-count // world_size)
+    tail = local.shape[1:]
+    buf = torch.zeros((per,) + tail, dtype=torch.float64, device=device)
+    if local.shape[0]:
+        buf[: local.shape[0]] = torch.as_tensor(local, dtype=torch.float64).to(device)
+    out = torch.empty((world_size * per,) + tail, dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_gather_into_tensor(out, buf)
+    else:
+        out.copy_(buf)
+    return out[:count].cpu().numpy()

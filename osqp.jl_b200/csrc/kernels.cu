@@ -11,6 +11,7 @@
 // Work split: block b owns a contiguous, nnz-balanced range of rows of A (m-range) and of
 // P / A' (n-range); all element-wise vector work on an index is done by the block owning it.
 #include "engine.cuh"
+#include "admm_rules.cuh"
 
 #include <cooperative_groups.h>
 #include <math.h>
@@ -19,15 +20,8 @@ namespace osqpb200 {
 
 namespace {
 
-constexpr double kInfty = 1e30;
-constexpr double kMinScaling = 1e-4, kMaxScaling = 1e4;
-constexpr double kRhoMin = 1e-6, kRhoMax = 1e6, kRhoEqOverIneq = 1e3, kRhoTol = 1e-4;
-constexpr double kDivisionTol = 1e-30;
-constexpr int kPrintInterval = 200;
 constexpr int kThreads = 512;  // threads per block of the cooperative kernels: 128 registers per thread
 
-constexpr long long ST_SOLVED = 1, ST_SOLVED_INACC = 2, ST_PINF_INACC = 3, ST_DINF_INACC = 4, ST_MAX_ITER = -2,
-                    ST_PINF = -3, ST_DINF = -4, ST_TIME_LIMIT = -6, ST_NON_CVX = -7, ST_UNSOLVED = -10;
 
 // ------------------------------------------------------------------ memory helpers
 // Matrix streams are read once per phase and never written inside a launch: non-coherent path,
@@ -410,13 +404,6 @@ __device__ __forceinline__ void group_reduce(Acc<NV> &acc, int lanes) {
   }
 }
 
-// ------------------------------------------------------------------ scaled/infeasibility info scalars
-struct InfoScalars {
-  double pri_t, pri_r, nz_t, nz_r, nAx_t, nAx_r, ndy_t, lhs, maxU_t, maxNegL_t;
-  double dua_t, dua_r, nq_t, nq_r, nAty_t, nAty_r, nPx_t, nPx_r, obj, ndx_t, qdx, nPdx_t, nAtdy_t;
-  double pri_res, dua_res, obj_val;  // what update_info publishes
-};
-
 // ------------------------------------------------------------------ PCG on K = P + sigma I + A' diag(rho) A
 // Chronopoulos-Gear single-reduction variant: 3 grid barriers per iteration
 // (after t = A u | after w = K u with delta = w.u | after the vector updates with gamma, |r|inf).
@@ -738,44 +725,6 @@ __device__ __noinline__ void compute_info(Grid &g, RedSmem &sm, const DevPtrs &d
   S.obj_val = c.scaling ? S.obj * cost_cinv : S.obj;
   S.pri_res = (d.m == 0) ? 0.0 : S.pri_t;
   S.dua_res = unscale ? cost_cinv * S.dua_t : S.dua_t;
-}
-
-// check_termination of libosqp 0.6.2; returns the new status or ST_UNSOLVED.
-__device__ __forceinline__ long long check_termination(const InfoScalars &S, const SolveCfg &c, int m, double cost_c,
-                                                       double cost_cinv, bool approximate) {
-  double eps_abs = c.eps_abs, eps_rel = c.eps_rel, eps_pinf = c.eps_prim_inf, eps_dinf = c.eps_dual_inf;
-  if (S.pri_res > kInfty || S.dua_res > kInfty) return ST_NON_CVX;
-  if (approximate) {
-    eps_abs *= 10; eps_rel *= 10; eps_pinf *= 10; eps_dinf *= 10;
-  }
-  const bool unscale = c.scaling && !c.scaled_termination;
-  bool prim_ok = false, dual_ok = false, prim_inf = false, dual_inf = false;
-  if (m == 0) prim_ok = true;
-  else {
-    const double eps_prim = eps_abs + eps_rel * fmax(S.nz_t, S.nAx_t);
-    if (S.pri_res < eps_prim) prim_ok = true;
-    else if (S.ndy_t > kDivisionTol && S.lhs < -eps_pinf * S.ndy_t) prim_inf = S.nAtdy_t < eps_pinf * S.ndy_t;
-  }
-  double mx = fmax(S.nq_t, fmax(S.nAty_t, S.nPx_t));
-  if (unscale) mx *= cost_cinv;
-  const double eps_dual = eps_abs + eps_rel * mx;
-  if (S.dua_res < eps_dual) dual_ok = true;
-  else {
-    const double cs = unscale ? cost_c : 1.0;
-    if (S.ndx_t > kDivisionTol && S.qdx < -cs * eps_dinf * S.ndx_t && S.nPdx_t < cs * eps_dinf * S.ndx_t)
-      dual_inf = !(S.maxU_t > eps_dinf * S.ndx_t) && !(S.maxNegL_t > eps_dinf * S.ndx_t);
-  }
-  if (prim_ok && dual_ok) return approximate ? ST_SOLVED_INACC : ST_SOLVED;
-  if (prim_inf) return approximate ? ST_PINF_INACC : ST_PINF;
-  if (dual_inf) return approximate ? ST_DINF_INACC : ST_DINF;
-  return ST_UNSOLVED;
-}
-
-__device__ __forceinline__ double rho_estimate(const InfoScalars &S, double rho) {
-  double pri = S.pri_r / (fmax(S.nz_r, S.nAx_r) + 1e-10);
-  double dua = S.dua_r / (fmax(S.nq_r, fmax(S.nAty_r, S.nPx_r)) + 1e-10);
-  double est = rho * sqrt(pri / (dua + 1e-10));
-  return fmin(fmax(est, kRhoMin), kRhoMax);
 }
 
 // Minv = 1 / (P_jj + sigma + sum_i rho_i A_ij^2) on rows [n0, n1)

@@ -1,0 +1,163 @@
+"""Batched engine (BASELINE config 5: many small MPC QPs, one sparsity pattern) -- include/osqp_b200.h osqp_batch_*.
+
+GPU tests compare every QP of a batch with the CPU oracle solving the same QP through the reference's single-QP
+API; CPU tests cover the sharding arithmetic and the world_size-2 gather (gloo) with the oracle standing in for the
+per-shard solver.
+"""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import problems
+
+FIXED = dict(verbose=False, adaptive_rho=False, check_termination=1, max_iter=4000, eps_abs=1e-6, eps_rel=1e-6,
+             polish=False)
+
+
+def oracle_solve(pkg, oracle_lib, prob, opts):
+    mdl = pkg.Model(lib=oracle_lib)
+    mdl.setup(**prob, **opts)
+    r = mdl.solve()
+    mdl.clean()
+    return r
+
+
+def test_shard_range_covers_batch(pkg):
+    for count in (1, 7, 8, 8192, 1000):
+        for world in (1, 2, 3, 8):
+            spans = [pkg.shard_range(count, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == count
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(hi - lo for lo, hi in spans) == -(-count // world)
+
+
+def _gloo_worker(rank, world, port, count, oracle_lib, out_dir):
+    import sys
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import __graft_entry__ as graft
+    pkg = graft.load_package()
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    batch = problems.mpc_batch_c5(count, 77)
+    lo, hi = pkg.shard_range(count, world, rank)
+    xs, its = [], []
+    for k in range(lo, hi):  # the oracle stands in for the per-shard GPU solver
+        r = oracle_solve(pkg, oracle_lib, problems.batch_instance(*batch, k), FIXED)
+        xs.append(r.x)
+        its.append([r.info.iter])
+    n = batch[1].shape[1]
+    x = pkg.batch.gather_sharded(np.array(xs).reshape(-1, n), count, world, rank)
+    it = pkg.batch.gather_sharded(np.array(its, dtype=np.float64).reshape(-1, 1), count, world, rank)
+    if rank == 0:
+        np.savez(os.path.join(out_dir, "gathered.npz"), x=x, it=it)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_batch_gather_world2_gloo(pkg, oracle_lib, tmp_path):
+    import torch.multiprocessing as mp
+
+    count = 5  # uneven shards: 3 + 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_gloo_worker, args=(2, port, count, oracle_lib, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "gathered.npz")
+    batch = problems.mpc_batch_c5(count, 77)
+    for k in range(count):
+        r = oracle_solve(pkg, oracle_lib, problems.batch_instance(*batch, k), FIXED)
+        assert np.array_equal(got["x"][k], r.x)
+        assert int(got["it"][k, 0]) == r.info.iter
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("opts,iter_tol", [
+    (FIXED, 1),
+    (dict(FIXED, eps_abs=1e-4, eps_rel=1e-4, check_termination=25), 0),
+    (dict(verbose=False, adaptive_rho_interval=25, eps_abs=1e-5, eps_rel=1e-5, max_iter=4000), 25),
+    (dict(FIXED, scaling=0), 1),
+])
+def test_mpc_batch_matches_oracle(pkg, engine_lib, oracle_lib, opts, iter_tol):
+    count = 48
+    batch = problems.mpc_batch_c5(count, 5)
+    bm = pkg.BatchModel(lib=engine_lib)
+    bm.setup(*batch, **opts)
+    res = bm.solve()
+    eps = opts.get("eps_abs", 1e-3)
+    for k in range(count):
+        o = oracle_solve(pkg, oracle_lib, problems.batch_instance(*batch, k), opts)
+        assert res.status[k] == o.info.status == "Solved", (k, res.status[k], o.info.status)
+        assert abs(int(res.iter[k]) - o.info.iter) <= iter_tol, (k, res.iter[k], o.info.iter)
+        assert np.max(np.abs(res.x[k] - o.x)) <= 10 * eps * (1 + np.max(np.abs(o.x))), k
+        assert np.max(np.abs(res.y[k] - o.y)) <= 10 * eps * (1 + np.max(np.abs(o.y))), k
+        assert abs(res.obj_val[k] - o.info.obj_val) <= 10 * eps * (1 + abs(o.info.obj_val)), k
+    bm.clean()
+
+
+@pytest.mark.gpu
+def test_batch_update_and_warm_start(pkg, engine_lib, oracle_lib):
+    # MPC receding horizon: new initial state -> new equality right-hand sides, warm start from the last solution
+    count = 16
+    Pp, Ap, Px, Ax, q, l, u = problems.mpc_batch_c5(count, 9)
+    bm = pkg.BatchModel(lib=engine_lib)
+    bm.setup(Pp, Ap, Px, Ax, q, l, u, **FIXED)
+    r1 = bm.solve()
+    rng = np.random.default_rng(3)
+    l2, u2 = l.copy(), u.copy()
+    shift = 0.05 * rng.standard_normal((count, 2))
+    l2[:, :2] += shift
+    u2[:, :2] += shift
+    q2 = q + 0.01 * rng.standard_normal(q.shape)
+    bm.update(q=q2, l=l2, u=u2)
+    r2 = bm.solve()  # warm-started from r1 (settings.warm_start defaults to 1)
+    assert np.sum(r2.iter) < np.sum(r1.iter) and np.all(r2.iter <= r1.iter + 2)
+    for k in range(count):
+        o = oracle_solve(pkg, oracle_lib, problems.batch_instance(Pp, Ap, Px, Ax, q2, l2, u2, k), FIXED)
+        assert res_close(r2.x[k], o.x, 1e-4) and res_close(r2.y[k], o.y, 1e-4), k  # 100 eps
+    # explicit warm start at the optimum: a handful of iterations (test/warm_start.jl:43-47)
+    bm.warm_start(x=r2.x, y=r2.y)
+    r3 = bm.solve()
+    assert np.all(r3.iter <= 10)
+    bm.clean()
+
+
+def res_close(a, b, tol):
+    return np.max(np.abs(a - b)) <= tol * (1 + np.max(np.abs(b)))
+
+
+@pytest.mark.gpu
+def test_batch_statuses_are_per_qp(pkg, engine_lib, oracle_lib):
+    # one infeasible QP (crossing input-rate and input bounds via the equality rhs) in the middle of a batch
+    count = 8
+    Pp, Ap, Px, Ax, q, l, u = problems.mpc_batch_c5(count, 11)
+    l, u = l.copy(), u.copy()
+    bad = 3
+    l[bad, 20:22] = 50.0   # x_1 >= 50 while the dynamics pin x_1 = Ad x_0 + Bd u_0 with |u_0| <= 1
+    u[bad, 20:22] = 60.0
+    opts = dict(FIXED, eps_abs=1e-5, eps_rel=1e-5, max_iter=2000)
+    bm = pkg.BatchModel(lib=engine_lib)
+    bm.setup(Pp, Ap, Px, Ax, q, l, u, **opts)
+    res = bm.solve()
+    o = oracle_solve(pkg, oracle_lib, problems.batch_instance(Pp, Ap, Px, Ax, q, l, u, bad), opts)
+    assert o.info.status == "Primal_infeasible"
+    assert res.status[bad] == "Primal_infeasible"
+    assert all(s == "Solved" for k, s in enumerate(res.status) if k != bad)
+    assert np.all(np.isnan(res.x[bad]))
+    bm.clean()
+
+
+@pytest.mark.gpu
+def test_batch_rejects_bad_input(pkg, engine_lib):
+    Pp, Ap, Px, Ax, q, l, u = problems.mpc_batch_c5(2, 1)
+    bm = pkg.BatchModel(lib=engine_lib)
+    with pytest.raises(RuntimeError):
+        bm.setup(Pp, Ap, Px, Ax, q, u + 1.0, u, **FIXED)  # l > u
+    Px_bad = Px.copy()
+    Px_bad[1, 0] = -5.0  # indefinite P
+    with pytest.raises(RuntimeError):
+        bm.setup(Pp, Ap, Px_bad, Ax, q, l, u, **dict(FIXED, sigma=1e-6))

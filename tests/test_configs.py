@@ -1,0 +1,80 @@
+"""BASELINE.json configs 3 and 4 at test sizes: CUDA engine vs CPU oracle through the reference's API.
+
+Config 3: Lasso as a QP, lambda sweep re-solved with osqp_update_lin_cost + retained iterates (warm start).
+Config 4: factor-model portfolio with polishing.  Constructions: problems.py.
+"""
+import numpy as np
+import pytest
+
+import problems
+
+pytestmark = pytest.mark.gpu
+
+
+def _models(pkg, engine_lib, oracle_lib, prob, opts):
+    out = {}
+    for name, lib in (("engine", engine_lib), ("oracle", oracle_lib)):
+        mdl = pkg.Model(lib=lib)
+        mdl.setup(**prob, **opts)
+        out[name] = mdl
+    return out
+
+
+@pytest.mark.parametrize("n_feat,n_samp,density", [(200, 1000, 0.15), (1000, 5000, 0.15)])
+def test_lasso_lambda_sweep_warm_started(pkg, engine_lib, oracle_lib, n_feat, n_samp, density):
+    prob, lam_max, q_of, n = problems.lasso_c3(n_feat, n_samp, density, 20263)
+    eps = 1e-4
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=10000, polish=False)
+    prob = dict(prob, q=q_of(lam_max))
+    mdl = _models(pkg, engine_lib, oracle_lib, prob, opts)
+    lams = np.logspace(0, -2, 5) * lam_max
+    prev_iters = None
+    for lam in lams:
+        res = {}
+        for name in ("engine", "oracle"):
+            mdl[name].update(q=q_of(lam))  # src/interface.jl:240-246; iterates are kept (warm_start = 1)
+            res[name] = mdl[name].solve()
+        e, o = res["engine"], res["oracle"]
+        assert e.info.status == o.info.status == "Solved", (lam, e.info.status, o.info.status)
+        # same optimum: objective and solution within the solver's tolerance (rho adapts, so iteration counts of
+        # the two linear-system backends may differ by an adaptive-rho interval)
+        assert abs(e.info.obj_val - o.info.obj_val) <= 20 * eps * (1 + abs(o.info.obj_val)), lam
+        assert np.max(np.abs(e.x - o.x)) <= 20 * eps * (1 + np.max(np.abs(o.x))), lam
+        assert abs(e.info.iter - o.info.iter) <= 50, (lam, e.info.iter, o.info.iter)
+        prev_iters = e.info.iter
+    # at lambda_max the Lasso solution is x = 0
+    assert prev_iters is not None
+    for m_ in mdl.values():
+        m_.clean()
+
+
+def test_lasso_at_lambda_max_is_zero(pkg, engine_lib):
+    prob, lam_max, q_of, n = problems.lasso_c3(300, 1500, 0.15, 7)
+    mdl = pkg.Model(lib=engine_lib)
+    # the objective is y'y (no 1/2), so x = 0 is optimal from lambda = 2 |Ad'b|inf on
+    mdl.setup(**dict(prob, q=q_of(2.1 * lam_max)), verbose=False, eps_abs=1e-6, eps_rel=1e-6, max_iter=20000,
+              adaptive_rho_interval=25)
+    r = mdl.solve()
+    assert r.info.status == "Solved"
+    assert np.max(np.abs(r.x[:300])) <= 1e-4
+    mdl.clean()
+
+
+@pytest.mark.parametrize("n_assets,k", [(500, 10), (4000, 40)])
+def test_portfolio_with_polish(pkg, engine_lib, oracle_lib, n_assets, k):
+    prob = problems.portfolio_c4(n_assets, k, 20264)
+    eps = 1e-4
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=10000, polish=True)
+    mdl = _models(pkg, engine_lib, oracle_lib, prob, opts)
+    e, o = mdl["engine"].solve(), mdl["oracle"].solve()
+    assert e.info.status == o.info.status == "Solved"
+    assert abs(e.info.obj_val - o.info.obj_val) <= 20 * eps * (1 + abs(o.info.obj_val))
+    x = e.x[:n_assets]
+    assert abs(np.sum(x) - 1.0) <= 1e-3 and np.min(x) >= -1e-3 and np.max(x) <= 1 + 1e-3
+    # polishing must not make the point worse than the ADMM iterate (libosqp accepts it only if residuals improve)
+    assert e.info.status_polish in (1, -1, 0)
+    if e.info.status_polish == 1:
+        assert e.info.pri_res <= 1e-6 and e.info.dua_res <= 1e-5
+        assert np.max(np.abs(e.x - o.x)) <= 1e-3 * (1 + np.max(np.abs(o.x)))
+    for m_ in mdl.values():
+        m_.clean()
