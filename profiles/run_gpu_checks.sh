@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_batch.py tests/test_configs.py -m gpu -q > gpurun_out/pytest_new.log 2>&1); tail -4 gpurun_out/pytest_new.log
-(timeout 400 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_b.json 2> gpurun_out/bench_b.err); python -c "
-import json; d=json.load(open('gpurun_out/bench_b.json')); print(d['value'], d['batch'])"; tail -3 gpurun_out/bench_b.err
+(timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1f_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1); tail -2 gpurun_out/ncu_bench.log | cut -c1-300
+(timeout 900 ncu --set full --clock-control none --import-source on -k regex:"admm_kernel" -s 1 -c 1 -o gpurun_out/r1f_admm python profiles/profile_driver.py --solves 2 --spmv-reps 1 > gpurun_out/ncu_admm.log 2>&1); tail -3 gpurun_out/ncu_admm.log
