@@ -97,6 +97,12 @@ def oracle_lib(pkg):
     lib = pkg.load_library(graft.ORACLE_LIB)
     lib.osqp_oracle_configure.argtypes = [C.c_longlong, C.c_double, C.c_longlong]
     lib.osqp_oracle_num_threads.restype = C.c_longlong
+    lib.osqp_oracle_set_num_threads.argtypes = [C.c_longlong]
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    lib.osqp_oracle_set_num_threads(cores)  # torchrun sets OMP_NUM_THREADS=1: use every host core we may run on
     return lib
 
 
@@ -149,7 +155,8 @@ def main():
     config = {"workload": workload, "n": args.n, "m": args.m, "seed": SEED,
               "parallelism": f"{world} independent QP(s), one per GPU, no collectives in the loop"}
 
-    graft.build()
+    if rank == 0 or not os.path.exists(graft.LIB):
+        graft.build()  # under torchrun the other ranks use what rank 0 built (or what travelled with the snapshot)
     pkg = graft.load_package()
 
     # ------------------------------------------------------------------ reference arm (CPU)
@@ -181,6 +188,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()  # rank 0 has finished building before anybody loads the library
     eng = pkg.load_library(graft.LIB)
     def profile(mdl):
         p = pkg.types.B200Profile()

@@ -993,6 +993,14 @@ void osqp_oracle_stats(OSQPWorkspace *work, c_float *out) {
   out[0] = w.lin ? w.lin->stat_a : 0;
   out[1] = w.lin ? w.lin->stat_b : 0;
 }
+// torchrun exports OMP_NUM_THREADS=1; the CPU baseline legs of bench.py ask for all host threads explicitly
+void osqp_oracle_set_num_threads(c_int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads((int)n);
+#else
+  (void)n;
+#endif
+}
 c_int osqp_oracle_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-(timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1f_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1); tail -2 gpurun_out/ncu_bench.log | cut -c1-300
-(timeout 900 ncu --set full --clock-control none --import-source on -k regex:"admm_kernel" -s 1 -c 1 -o gpurun_out/r1f_admm python profiles/profile_driver.py --solves 2 --spmv-reps 1 > gpurun_out/ncu_admm.log 2>&1); tail -3 gpurun_out/ncu_admm.log
+nvidia-smi -L
+(timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err); tail -c 1500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
+(timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err); tail -c 600 gpurun_out/bench_ref_n2.json
