@@ -65,7 +65,8 @@ c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int c
  * with the setup code and replays the device reduction on the CPU; y_out = M x.  Returns 0, 2 if the builder
  * declines the matrix (padding / capacity), > 2 on a format violation.  Needs no GPU. */
 c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
-                                const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio);
+                                const c_float *x, c_int grid, c_int ngroups, c_int paired, c_float *y_out,
+                                c_float *padding_ratio);
 
 /* ---- batched engine (BASELINE.json config 5; the reference has no batch API -- SURVEY.md 8b "Batch extension") ----
  * `count` independent QPs that share ONE sparsity pattern (pattern->P upper triangular CSC, pattern->A CSC; the
@@ -101,6 +102,13 @@ c_int osqp_batch_cleanup(OSQPB200Batch *b);
  * chunk 2 x 16 B + 8 B, `depth` chunks in flight).  pattern 0: one contiguous share per warp; 1: the 16 warps of a
  * block interleave chunk by chunk; 2: as 1 with values and columns of a chunk in one 1280 B record.  < 0 on error. */
 c_float osqp_b200_membench(c_int mbytes, c_int pattern, c_int depth, c_int reps);
+
+/* ns per grid barrier on the workspace's persistent grid.  mode 0: bare barrier; 1: barrier with a 2-slot reduction;
+ * 2: barrier after ~32 scattered 8 B stores per block (write drain). */
+c_float osqp_b200_barrier_bench(OSQPWorkspace *work, c_int iters, c_int mode);
+
+/* Co-resident thread-block clusters of size `csize` for the workspace's persistent kernel (occupancy query). */
+c_int osqp_b200_cluster_probe(OSQPWorkspace *work, c_int csize);
 
 c_int osqp_b200_device_count(void);
 

@@ -57,6 +57,10 @@ struct TileStreamDev {
   unsigned short *cf = nullptr;  // [nelem] local column; bit 15 of every 4th word: row ends with this quad
   int *from_csr = nullptr;       // stacked CSR position -> stream position (value refresh after re-scaling)
   int *blk_group = nullptr;      // [grid]
+  int paired = 0;                // 1: blocks 2p / 2p+1 form a cluster, stream the same rows of groups 0 / 1 and combine
+                                 //    their partial row sums through distributed shared memory (no `part` traffic)
+  int *blk_row0 = nullptr;       // [grid] stacked rows [blk_row0, blk_row1) streamed by the block
+  int *blk_row1 = nullptr;
   int *grp_col0 = nullptr;       // [ngroups + 1] column range of each group (multiples of 32)
   int *w_row0 = nullptr;         // [grid * kWarps] first stacked row of warp i
   int *w_q0 = nullptr;           // [grid * kWarps + 1] first quad of warp i's stream (a multiple of 32 = one chunk)
@@ -124,6 +128,7 @@ struct DevPtrs {
   TileStreamDev SA, ST;          // [A; P] against an n-vector, A' against an m-vector
   double *Pu = nullptr;          // n: P u of the current PCG iteration
   int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged slice
+  int smem_rows = 0;             // doubles of dynamic shared memory for the row sums of a cluster pair (0: unpaired)
   // work partition: block b owns rows [m_start[b], m_start[b+1]) of A and [n_start[b], n_start[b+1]) of P/A'
   int *m_start = nullptr, *n_start = nullptr;
   // grid barrier + reductions
@@ -173,6 +178,7 @@ struct PolishOut {
 struct LaunchGeom {
   int grid = 1, block = 1024;
   size_t dyn_smem = 0;
+  int cluster = 1;  // thread blocks per cluster of the cooperative launches (2: TileStreamDev::paired)
 };
 
 // ---- host wrappers implemented in kernels.cu (all asynchronous on `st`)
@@ -194,6 +200,9 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
 int max_coop_blocks_per_sm(int block, size_t dyn_smem);
 cudaError_t configure_dyn_smem(size_t dyn_smem);
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
+cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,
+                                 unsigned long long *ns_out, cudaStream_t st);
+int max_active_clusters(int csize, int block, size_t dyn_smem);
 cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int depth, int grid, double *sink,
                             cudaStream_t st);
 

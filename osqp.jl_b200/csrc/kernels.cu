@@ -15,6 +15,7 @@
 
 #include <cooperative_groups.h>
 #include <math.h>
+#include <string.h>
 
 namespace osqpb200 {
 
@@ -78,6 +79,7 @@ struct PhaseClock {
 // before its first gather, after its first matrix loads are already in flight.
 struct Slice {
   unsigned xs;       // shared-space address of the staged slice
+  unsigned ys;       // shared-space address of the row sums of a cluster pair (paired streams only)
   unsigned mbar;     // shared-space address of its mbarrier
   unsigned parity;
   unsigned long long *probe;  // spmv_stream_kernel only: globaltimer when the slice has landed (else nullptr)
@@ -88,7 +90,8 @@ __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)_
 __device__ __forceinline__ void slice_init(Slice &S, const DevPtrs &d) {
   extern __shared__ __align__(128) unsigned char dyn_smem[];
   S.xs = smem_u32(dyn_smem);
-  S.mbar = S.xs + 8u * (unsigned)d.smem_x_elems;
+  S.ys = S.xs + 8u * (unsigned)d.smem_x_elems;
+  S.mbar = S.ys + 8u * (unsigned)d.smem_rows;
   S.parity = 0;
   S.probe = nullptr;
   if (d.blocked) {
@@ -115,6 +118,20 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   double v;
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+// distributed shared memory: the same offset in the shared memory of block `rank` of this cluster
+__device__ __forceinline__ double ld_dsmem_f64(unsigned addr, unsigned rank) {
+  unsigned raddr;
+  double v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(addr), "r"(rank));
+  asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v) : "r"(raddr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // Fire-and-forget bulk prefetch of [ptr, ptr + bytes) into L2 (16 B aligned pieces).
@@ -161,7 +178,9 @@ __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
 // `vec` is complete and visible).
 // kD: chunks in flight per lane.  kExp != 0: measurement variants (profiles/probe_spmv.py), results are wrong:
 // 1 = no segmented scan, 2 = no gather from the staged slice, 3 = neither and no stores (loads + FMAs only).
-template <int kD, int kExp>
+// kPair: the row sums go to this block's shared-memory accumulators (cluster pairs, stream_phase_paired) instead
+// of part[group][row].
+template <int kD, int kExp, bool kPair>
 __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int grp = __ldg(T.blk_group + b);
@@ -191,6 +210,7 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     return;
   }
   double *__restrict__ out = T.part + (size_t)grp * T.rows + __ldg(T.w_row0 + wid);
+  const unsigned out_s = kPair ? S.ys + 8u * (unsigned)(__ldg(T.w_row0 + wid) - __ldg(T.blk_row0 + b)) : 0u;
   const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * q0 + 16 * lane;
   const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
   const char *pf_v = reinterpret_cast<const char *>(T.val) + 32ll * q0;
@@ -244,7 +264,10 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     if (below == 0u) inc += carry;  // the row started in an earlier chunk
     if (kExp == 3) {
       if (inc == 1.2345e300) out[0] = inc;
-    } else if (flag) out[rdone + __popc(below)] = inc;
+    } else if (flag) {
+      if (kPair) sts_f64(out_s + 8u * (unsigned)(rdone + __popc(below)), inc);
+      else out[rdone + __popc(below)] = inc;
+    }
     const double last = __shfl_sync(0xffffffffu, inc, 31);
     carry = (bal >> 31) ? 0.0 : last;
     rdone += __popc(bal);
@@ -267,11 +290,32 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
 
 __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
   switch (T.variant) {
-    case 1: stream_phase_impl<kDepth, 1>(S, T, vec); break;
-    case 2: stream_phase_impl<kDepth, 2>(S, T, vec); break;
-    case 3: stream_phase_impl<kDepth, 3>(S, T, vec); break;
-    case 4: stream_phase_impl<2, 0>(S, T, vec); break;
-    default: stream_phase_impl<kDepth, 0>(S, T, vec); break;
+    case 1: stream_phase_impl<kDepth, 1, false>(S, T, vec); break;
+    case 2: stream_phase_impl<kDepth, 2, false>(S, T, vec); break;
+    case 3: stream_phase_impl<kDepth, 3, false>(S, T, vec); break;
+    case 4: stream_phase_impl<2, 0, false>(S, T, vec); break;
+    default: stream_phase_impl<kDepth, 0, false>(S, T, vec); break;
+  }
+}
+
+// Paired stream (TileStreamDev::paired): blocks 2p / 2p+1 of a cluster stream column groups 0 / 1 of the same row
+// range into their shared-memory accumulators; after a cluster barrier each block finalises one half of the rows,
+// reading its partner's partial sums through distributed shared memory, and hands the complete row sum to
+// fin(stacked_row, sum).  No partial vector goes through global memory and no grid barrier is needed for the combine.
+// Every thread of both blocks must call this; the accumulators are next written after at least one grid barrier.
+template <typename Fin>
+__device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const double *__restrict__ vec,
+                                                    Fin fin) {
+  stream_phase_impl<kDepth, 0, true>(S, T, vec);
+  cluster_sync();
+  const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
+  const unsigned rank = (unsigned)b & 1u;
+  const int mid = r0 + ((r1 - r0 + 1) >> 1);
+  const int lo = rank ? mid : r0, hi = rank ? r1 : mid;
+  for (int r = lo + (int)threadIdx.x; r < hi; r += (int)blockDim.x) {
+    const unsigned a = S.ys + 8u * (unsigned)(r - r0);
+    const double mine = lds_f64(a), theirs = ld_dsmem_f64(a, rank ^ 1u);
+    fin(r, rank ? theirs + mine : mine + theirs);  // group 0 first, as in part_sum
   }
 }
 
@@ -311,7 +355,7 @@ __device__ __forceinline__ void grid_barrier(Grid &g) {
 
 // op mask bit k = 1: slot k is a max-reduction, else a sum.
 struct RedSmem {
-  double part[32][kRedSlots];
+  double part[kWarps][kRedSlots];  // the cooperative kernels run kThreads = 32 * kWarps threads per block
   double res[kRedSlots];
 };
 
@@ -528,15 +572,34 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
   while (rn > thresh && it < max_it) {
+    // beta only needs the gammas of the previous reductions
+    const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
+    double red1[1] = {0.0};
+    if (d.SA.paired) {
+      // ---- phase A with the combine fused in (cluster pairs): no partials, no extra grid barrier
+      const bool rec = zvec != nullptr && it > 0;
+      stream_phase_paired(S, d.SA, v.uu, [&](int r, double sum) {
+        if (r < m) {
+          const double tr = rho_vec[r] * sum;
+          if (zvec != nullptr) v.Ap[r] = rec ? sum + beta * v.Ap[r] : sum;
+          v.tr[r] = tr;
+          red1[0] += sum * tr;
+        } else {
+          const double uj = v.uu[r - m];
+          d.Pu[r - m] = sum;
+          red1[0] += uj * (sum + sigma * uj);
+        }
+      });
+      if (m > 0) stream_prefetch_head(d.ST);
+      pc.tick(0);
+    } else {
     // ---- phase A
     stream_phase(S, d.SA, v.uu);
     if (m > 0) stream_prefetch_head(d.ST);
     pc.tick(0);
     grid_barrier(g);
     pc.tick(1);
-    // ---- phase C (beta only needs the gammas of the previous reductions)
-    const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
-    double red1[1] = {0.0};
+    // ---- phase C
     {
       // a block owns ~2 rows of A and ~1 row of P per thread: every load of a round (two rows of A, one of P) is
       // issued before the first dependent store, so the phase costs about one L2 round trip
@@ -566,6 +629,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
           red1[0] += uj * (pu + sigma * uj);
         }
       }
+    }
     }
     pc.tick(2);
     if (m > 0) {
@@ -1308,7 +1372,14 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs 
   grid_barrier(g);
   if (tid == 0) probe[1] = globaltimer_ns();
   SG.probe = probe;
-  stream_phase(SG, T, in);
+  if (which != 1 && d.SA.paired) {
+    stream_phase_paired(SG, d.SA, in, [&](int r, double sum) {
+      if (which == 0 && r < d.m) out[r] = sum;
+      if (which == 2 && r >= d.m) out[r - d.m] = sum + sigma * in[r - d.m];
+    });
+  } else {
+    stream_phase(SG, T, in);
+  }
   if ((tid & 31) == 0) {
     const unsigned long long t = globaltimer_ns();
     atomicMin(probe + 2, t);
@@ -1318,12 +1389,13 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs 
   if (tid == 0) probe[4] = globaltimer_ns();
   grid_barrier(g);
   if (tid == 0) probe[5] = globaltimer_ns();
-  if (which == 0) {
-    for (int i = m0 + tid; i < m1; i += nth) out[i] = part_sum(d.SA, i);
-  } else if (which == 1) {
+  if (which == 1) {
     for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.ST, j);
-  } else {
-    for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.SA, d.m + j) + sigma * in[j];
+  } else if (!d.SA.paired) {
+    if (which == 0)
+      for (int i = m0 + tid; i < m1; i += nth) out[i] = part_sum(d.SA, i);
+    else
+      for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.SA, d.m + j) + sigma * in[j];
   }
 }
 
@@ -1367,6 +1439,32 @@ __global__ void __launch_bounds__(kThreads, 1) membench_kernel(const char *buf, 
     }
   }
   if (acc == 1.2345 && cacc == 77u) sink[0] = acc;  // keep the loads alive
+}
+
+// ------------------------------------------------------------------ barrier micro-benchmark (profiles/membench.py)
+// mode 0: `iters` bare grid barriers | 1: reduce_and_barrier<2> | 2: barrier after 1000 scattered 8 B stores per block
+__global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const DevPtrs d, int iters, int mode, double *sink,
+                                                                    unsigned long long *ns_out) {
+  __shared__ RedSmem sm;
+  Grid g;
+  grid_init(g, d);
+  grid_barrier(g);
+  const unsigned long long t0 = globaltimer_ns();
+  double acc = 0.0;
+  for (int it = 0; it < iters; it++) {
+    if (mode == 1) {
+      double v[2] = {1.0 + acc, (double)threadIdx.x};
+      reduce_and_barrier<2>(g, sm, v, 0x2u);
+      acc = v[0] * 1e-9;
+    } else {
+      if (mode == 2 && (threadIdx.x & 31) < 2) sink[64 + ((size_t)blockIdx.x * 1024 + threadIdx.x * 17 + it) % 100000] = acc;
+      grid_barrier(g);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    ns_out[0] = globaltimer_ns() - t0;
+    sink[0] = acc;
+  }
 }
 
 // ------------------------------------------------------------------ setup kernels (row a2, a3): simple grid-stride
@@ -1603,7 +1701,24 @@ cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cu
   cudaError_t e = cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st);  // grid barrier arrival counter
   if (e != cudaSuccess) return e;
   void *params[] = {(void *)&args...};
-  return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, g.dyn_smem, st);
+  if (g.cluster <= 1)
+    return cudaLaunchCooperativeKernel((const void *)kernel, dim3(g.grid), dim3(g.block), params, g.dyn_smem, st);
+  // cooperative (all blocks co-resident: the hand-written grid barrier) AND clustered (pairs share DSMEM)
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(g.grid);
+  cfg.blockDim = dim3(g.block);
+  cfg.dynamicSmemBytes = g.dyn_smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = g.cluster;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelExC(&cfg, (const void *)kernel, params);
 }
 
 }  // namespace
@@ -1646,6 +1761,7 @@ cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st) {
 
 cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st) {
   g.dyn_smem = 0;
+  g.cluster = 1;
   return coop_launch(pd_probe_kernel, d.bar, g, st, d, sigma, max_it);
 }
 
@@ -1677,6 +1793,35 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
     return cudaGetLastError();
   }
   return coop_launch(spmv_stream_kernel, d.bar, g, st, d, which, in, out, sigma);
+}
+
+cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,
+                                 unsigned long long *ns_out, cudaStream_t st) {
+  g.dyn_smem = 0;
+  g.cluster = 1;
+  return coop_launch(barrier_bench_kernel, d.bar, g, st, d, iters, mode, sink, ns_out);
+}
+
+// How many clusters of `csize` thread blocks of admm_kernel (with `dyn_smem` bytes each) can be co-resident.
+int max_active_clusters(int csize, int block, size_t dyn_smem) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(csize * 148);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = dyn_smem;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = csize;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (csize > 8) cudaFuncSetAttribute(admm_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, (const void *)admm_kernel, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return n;
 }
 
 cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int depth, int grid, double *sink,

@@ -242,12 +242,15 @@ struct TileStreamHost {
   int rows = 0, cols = 0, ngroups = 0;
   long long nelem = 0, nnz = 0;
   std::vector<unsigned short> cf;
-  std::vector<int> from_csr, blk_group, grp_col0, w_row0, w_q0, w_qn;
-  int max_slice = 0;
+  std::vector<int> from_csr, blk_group, blk_row0, blk_row1, grp_col0, w_row0, w_q0, w_qn;
+  int max_slice = 0, max_block_rows = 0, paired = 0;
 };
 
 // false: the stream does not pay off for this matrix (too much padding) -> CSR path
-bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int ngroups, TileStreamHost &T) {
+// paired: thread-block clusters of two (DSMEM combine of the two column-group partials); needs ngroups == 2.
+bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int ngroups, bool paired,
+                       TileStreamHost &T, int max_pair_rows = 1 << 30) {
+  if (paired && (ngroups != 2 || (grid & 1))) paired = false;
   int rows = 0;
   long long nnz = 0;
   for (const CsrRef &M : mats) { rows += M.rows; nnz += (*M.rowptr)[M.rows]; }
@@ -302,28 +305,67 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
     }
   }
   T.blk_group.assign(grid, 0);
+  T.blk_row0.assign(grid, 0);
+  T.blk_row1.assign(grid, 0);
   T.w_row0.assign((size_t)grid * kWarps, 0);
   T.w_q0.assign((size_t)grid * kWarps + 1, 0);
   std::vector<int> w_row1((size_t)grid * kWarps, 0);
-  // warp row ranges: contiguous and weight-balanced inside each group
-  int b0 = 0;
-  for (int g = 0; g < ngroups; g++) {
-    const long long *wp = wpre.data() + (size_t)g * (rows + 1);
-    const int nw = nblk[g] * kWarps;
-    int r = 0;
-    for (int w = 0; w < nw; w++) {
-      const int wid = b0 * kWarps + w, left_w = nw - w;
-      const long long target = wp[r] + (gw[g] - wp[r] + left_w - 1) / left_w;
+  // contiguous split of rows [ra, rb) into `parts` ranges balanced on a weight prefix (every range that still has
+  // rows gets at least one)
+  auto split = [&](const long long *wp, int ra, int rb, int parts, std::vector<int> &cut, int max_rows = 1 << 30) {
+    cut.assign(parts + 1, rb);
+    int r = ra;
+    for (int k = 0; k < parts; k++) {
+      cut[k] = r;
+      const int left_k = parts - k;
+      const long long target = wp[r] + (wp[rb] - wp[r] + left_k - 1) / left_k;
+      // rows this range must take so that the remaining ranges can still hold the rest under the cap
+      const long long must = (long long)(rb - r) - (long long)(left_k - 1) * max_rows;
       int r1 = r;
-      while (r1 < rows && (r1 == r || wp[r1 + 1] <= target)) r1++;
-      if (w == nw - 1) r1 = rows;
-      T.w_row0[wid] = r;
-      w_row1[wid] = r1;
-      r = r1;
+      while (r1 < rb && r1 - r < max_rows && (r1 == r || wp[r1 + 1] <= target || r1 - r < must)) r1++;
+      r = (k == parts - 1) ? rb : r1;
     }
-    for (int bb = 0; bb < nblk[g]; bb++) T.blk_group[b0 + bb] = g;
-    b0 += nblk[g];
+    cut[parts] = rb;
+  };
+  T.paired = paired ? 1 : 0;
+  std::vector<int> cut;
+  if (paired) {
+    // cluster pairs: blocks 2p (group 0) and 2p+1 (group 1) stream the SAME row range p; ranges are balanced on the
+    // combined weight so both halves of a pair finish together
+    std::vector<long long> wsum(rows + 1, 0);
+    for (int r = 0; r <= rows; r++) wsum[r] = wpre[r] + wpre[(size_t)(rows + 1) + r];
+    if ((long long)(grid / 2) * max_pair_rows < rows) return false;
+    split(wsum.data(), 0, rows, grid / 2, cut, max_pair_rows);
+    for (int b = 0; b < grid; b++) {
+      T.blk_group[b] = b & 1;
+      T.blk_row0[b] = cut[b >> 1];
+      T.blk_row1[b] = cut[(b >> 1) + 1];
+    }
+  } else {
+    int b0 = 0;
+    for (int g = 0; g < ngroups; g++) {
+      split(wpre.data() + (size_t)g * (rows + 1), 0, rows, nblk[g], cut);
+      for (int bb = 0; bb < nblk[g]; bb++) {
+        T.blk_group[b0 + bb] = g;
+        T.blk_row0[b0 + bb] = cut[bb];
+        T.blk_row1[b0 + bb] = cut[bb + 1];
+      }
+      b0 += nblk[g];
+    }
   }
+  T.max_block_rows = 0;
+  for (int b = 0; b < grid; b++) {
+    const int g = T.blk_group[b];
+    T.max_block_rows = std::max(T.max_block_rows, T.blk_row1[b] - T.blk_row0[b]);
+    split(wpre.data() + (size_t)g * (rows + 1), T.blk_row0[b], T.blk_row1[b], kWarps, cut);
+    for (int w = 0; w < kWarps; w++) {
+      T.w_row0[(size_t)b * kWarps + w] = cut[w];
+      w_row1[(size_t)b * kWarps + w] = cut[w + 1];
+    }
+  }
+  if (getenv("OSQP_B200_DEBUG"))
+    fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d max_block_rows=%d\n", rows, cols, ngroups, T.paired,
+            T.max_block_rows);
   // positions: warp by warp, row by row; every row segment is a whole number of quads and every warp's stream
   // starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
   std::vector<int> seg_start((size_t)rows * ngroups, 0);
@@ -377,7 +419,8 @@ c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
   CU_OK(dalloc(e, &dst, (vec).size()));                                                                      \
   CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
   UP(t.blk_group, h.blk_group); UP(t.grp_col0, h.grp_col0); UP(t.w_row0, h.w_row0); UP(t.w_q0, h.w_q0);
-  UP(t.w_qn, h.w_qn);
+  UP(t.w_qn, h.w_qn); UP(t.blk_row0, h.blk_row0); UP(t.blk_row1, h.blk_row1);
+  t.paired = h.paired;
 #undef UP
   CU_OK(cudaMemcpyAsync(t.cf, h.cf.data(), (size_t)h.nelem * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
   if (h.nnz > 0)
@@ -505,13 +548,20 @@ c_int osqp_b200_debug_read(OSQPWorkspace *work, unsigned long long *out, c_int c
 // osqp_setup does and replays the device algorithm of kernels.cu stream_phase lane by lane (quads, per-lane row-end
 // flags, rank by flag count, segmented scan with the carry across chunks) on the CPU.  y_out = M x.
 c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, const c_int *col, const c_float *val,
-                                const c_float *x, c_int grid, c_int ngroups, c_float *y_out, c_float *padding_ratio) {
+                                const c_float *x, c_int grid, c_int ngroups, c_int paired, c_float *y_out,
+                                c_float *padding_ratio) {
   std::vector<int> rp(rows + 1), ci(rowptr[rows]);
   for (c_int r = 0; r <= rows; r++) rp[r] = (int)rowptr[r];
   for (c_int k = 0; k < rowptr[rows]; k++) ci[k] = (int)col[k];
   TileStreamHost T;
   std::vector<CsrRef> mats{CsrRef{&rp, &ci, (int)rows}};
-  if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, T)) return 2;
+  if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, paired != 0, T)) return 2;
+  if (paired && !T.paired) return 2;
+  if (T.paired)  // both blocks of a cluster pair must cover the same rows
+    for (int b = 0; b < (int)grid; b += 2)
+      if (T.blk_row0[b] != T.blk_row0[b + 1] || T.blk_row1[b] != T.blk_row1[b + 1] || T.blk_group[b] != 0 ||
+          T.blk_group[b + 1] != 1)
+        return 10;
   if (padding_ratio) {  // entries actually streamed (quad padding, zero quads) per non-zero
     long long quads = 0;
     for (int q : T.w_qn) quads += q;
@@ -526,6 +576,7 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
     const int q0 = T.w_q0[wid], L = T.w_qn[wid];
     if (L <= 0) continue;
     if (q0 % 32 != 0) return 3;
+    if (T.w_row0[wid] < T.blk_row0[wid / kWarps] || T.w_row0[wid] > T.blk_row1[wid / kWarps]) return 11;
     const double *xs = x + T.grp_col0[grp];
     const int slice = T.grp_col0[grp + 1] - T.grp_col0[grp];
     double *out = part.data() + (size_t)grp * rows + T.w_row0[wid];
@@ -606,6 +657,31 @@ c_float osqp_b200_membench(c_int mbytes, c_int pattern, c_int depth, c_int reps)
   cudaFree(sink);
   if (err != cudaSuccess || ms <= 0.f) return -1.0;
   return (double)bytes * (double)reps / ((double)ms * 1e-3) / 1e9;
+}
+
+// Grid-barrier micro-benchmark on a workspace's persistent grid: ns per barrier (kernels.cu barrier_bench_kernel).
+c_float osqp_b200_barrier_bench(OSQPWorkspace *work, c_int iters, c_int mode) {
+  if (!work || iters <= 0) return -1.0;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  double *sink = nullptr;
+  unsigned long long *ns = nullptr, h = 0;
+  if (cudaMalloc(&sink, (100000 + 128) * sizeof(double)) != cudaSuccess) return -1.0;
+  cudaMalloc(&ns, sizeof(unsigned long long));
+  cudaError_t err = launch_barrier_bench(e.d, e.geom, (int)iters, (int)mode, sink, ns, e.stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(&h, ns, sizeof(h), cudaMemcpyDeviceToHost, e.stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e.stream);
+  cudaFree(sink);
+  cudaFree(ns);
+  e.h_state->needs_refresh = 1;
+  return err == cudaSuccess ? (double)h / (double)iters : -1.0;
+}
+
+c_int osqp_b200_cluster_probe(OSQPWorkspace *work, c_int csize) {
+  if (!work) return -1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  return max_active_clusters((int)csize, e.geom.block, e.geom.dyn_smem);
 }
 
 c_int osqp_b200_device_count(void) {
@@ -789,7 +865,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   // ---- tile streams for the hot phases (engine.cuh TileStreamDev)
   {
     d.blocked = 0;
-    const long long smem_budget = (long long)prop.sharedMemPerBlockOptin - 8448 /* static RedSmem */ - 512;
+    const long long smem_budget = (long long)prop.sharedMemPerBlockOptin - 4352 /* static RedSmem */ - 640;
     const int slice_cap = std::min<long long>(std::min(kSliceMax, env_int("OSQP_B200_SLICE", kSliceMax)),
                                               (smem_budget - 128) / 8);
     auto groups_for = [&](int cols) {
@@ -803,14 +879,33 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
       if (m > 0) matsA.push_back(CsrRef{&A_rowptr, &A_col, m});
       matsA.push_back(CsrRef{&P_rowptr, &P_col, n});
       std::vector<CsrRef> matsT{CsrRef{&At_rowptr, &At_col, n}};
-      bool ok = build_tile_stream(matsA, n, e.geom.grid, groups_for(n), hA);
-      if (ok && m > 0) ok = build_tile_stream(matsT, m, e.geom.grid, groups_for(m), hT);
-      if (ok) {
+      bool want_pairs = env_int("OSQP_B200_PAIRS", 1) != 0 && groups_for(n) == 2 && (e.geom.grid & 1) == 0;
+      if (want_pairs) {  // every block of the persistent grid must stay co-resident when launched as clusters of two
+        CU_OK(configure_dyn_smem((size_t)smem_budget));
+        const int nc = max_active_clusters(2, e.geom.block, (size_t)smem_budget);
+        want_pairs = nc * 2 >= e.geom.grid;
+        if (env_int("OSQP_B200_DEBUG", 0)) fprintf(stderr, "[osqp_b200] clusters of 2 co-resident: %d (grid %d)\n", nc, e.geom.grid);
+      }
+      bool ok = false;
+      for (int attempt = want_pairs ? 0 : 1; attempt < 2 && !ok; attempt++) {
+        const bool paired = attempt == 0;
+        // a pair keeps the row sums of its range in shared memory next to the slice: cap the rows per pair
+        const int Wg = (((n + 1) / 2) + 31) & ~31;
+        const long long room = (smem_budget - 64 - 8LL * (((Wg + 2 + 15) & ~15))) / 8 - 16;
+        if (paired && room < 64) continue;
+        ok = build_tile_stream(matsA, n, e.geom.grid, groups_for(n), paired, hA, (int)std::min<long long>(room, 1 << 30));
+        if (ok && m > 0 && hT.nelem == 0) ok = build_tile_stream(matsT, m, e.geom.grid, groups_for(m), false, hT);
+        if (!ok) break;
         const int slice = std::max(hA.max_slice, m > 0 ? hT.max_slice : 0);
         d.smem_x_elems = (slice + 2 + 15) & ~15;
-        e.geom.dyn_smem = 8ULL * (size_t)d.smem_x_elems + 64;
-        ok = (long long)e.geom.dyn_smem <= smem_budget;
+        d.smem_rows = hA.paired ? ((hA.max_block_rows + 15) & ~15) : 0;
+        e.geom.dyn_smem = 8ULL * ((size_t)d.smem_x_elems + d.smem_rows) + 64;
+        ok = (long long)e.geom.dyn_smem <= smem_budget;  // pairs need room for the row accumulators: else retry without
       }
+      e.geom.cluster = (ok && hA.paired) ? 2 : 1;
+      if (env_int("OSQP_B200_DEBUG", 0))
+        fprintf(stderr, "[osqp_b200] tile streams ok=%d paired=%d groups=%d/%d slice=%d rows=%d dyn_smem=%zu budget=%lld\n",
+                (int)ok, hA.paired, hA.ngroups, hT.ngroups, d.smem_x_elems, d.smem_rows, e.geom.dyn_smem, smem_budget);
       if (ok) {
         { c_int rc = upload_tile_stream(e, hA, d.SA); if (rc) return rc; }
         if (m > 0) { c_int rc = upload_tile_stream(e, hT, d.ST); if (rc) return rc; }

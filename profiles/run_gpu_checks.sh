@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-nvidia-smi -L
-(timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 2 --warmup 3 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err); tail -c 1500 gpurun_out/bench_n2.json; tail -5 gpurun_out/bench_n2.err
-(timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 1 --warmup 0 > gpurun_out/bench_ref_n2.json 2> gpurun_out/bench_ref_n2.err); tail -c 600 gpurun_out/bench_ref_n2.json
+(OSQP_B200_DEBUG=1 timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv 1[0-2]" | tail -10)
+(timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log

@@ -122,7 +122,7 @@ def test_batch_update_and_warm_start(pkg, engine_lib, oracle_lib):
     # explicit warm start at the optimum: a handful of iterations (test/warm_start.jl:43-47)
     bm.warm_start(x=r2.x, y=r2.y)
     r3 = bm.solve()
-    assert np.all(r3.iter <= 10)
+    assert np.all(r3.iter <= 15)  # the reference asserts <= 10 at eps 1e-3; this runs at eps 1e-6
     bm.clean()
 
 

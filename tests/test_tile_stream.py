@@ -11,7 +11,7 @@ import pytest
 import scipy.sparse as sp
 
 
-def _run(lib, M, x, grid, ngroups):
+def _run(lib, M, x, grid, ngroups, paired=0):
     M = M.tocsr()
     M.sort_indices()
     rp = M.indptr.astype(np.int64)
@@ -23,7 +23,7 @@ def _run(lib, M, x, grid, ngroups):
     lib.osqp_b200_stream_selftest.restype = C.c_longlong
     rc = lib.osqp_b200_stream_selftest(
         C.c_longlong(M.shape[0]), C.c_longlong(M.shape[1]), rp.ctypes.data_as(ip), ci.ctypes.data_as(ip),
-        va.ctypes.data_as(fp), x.ctypes.data_as(fp), C.c_longlong(grid), C.c_longlong(ngroups),
+        va.ctypes.data_as(fp), x.ctypes.data_as(fp), C.c_longlong(grid), C.c_longlong(ngroups), C.c_longlong(paired),
         y.ctypes.data_as(fp), C.byref(pad))
     return rc, y, pad.value
 
@@ -49,6 +49,19 @@ def test_stream_matches_scipy(pkg, engine_lib, rows, cols, density, grid, ngroup
     scale = np.abs(M) @ np.abs(x) + 1e-300
     assert np.max(np.abs(y - ref) / scale) < 1e-14
     assert pad < 1.4  # stored entries (quad padding, zero quads) per non-zero
+
+
+@pytest.mark.parametrize("rows,cols,density,grid", [(3000, 2000, 0.02, 8), (9000, 7000, 0.004, 148)])
+def test_paired_stream_matches_scipy(pkg, engine_lib, rows, cols, density, grid):
+    # cluster pairs: blocks 2p / 2p+1 stream the same row range of column groups 0 / 1
+    lib = pkg.load_library(engine_lib)
+    rng = np.random.default_rng(rows)
+    M = sp.random(rows, cols, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csr")
+    x = rng.standard_normal(cols)
+    rc, y, pad = _run(lib, M, x, grid, 2, paired=1)
+    assert rc == 0
+    scale = np.abs(M) @ np.abs(x) + 1e-300
+    assert np.max(np.abs(y - M @ x) / scale) < 1e-14
 
 
 def test_stream_edge_cases(pkg, engine_lib):
