@@ -494,6 +494,472 @@ __global__ void batch_solve_kernel(BatchDims d, double *state, SolveCfg c, long 
   }
 }
 
+// =================================================================== fast path: one WARP per QP (n <= 32, m <= 64)
+// Lane j owns entry j of every n-vector and entries j, j + 32 of every m-vector in registers; the matrices stay sparse
+// (the shared pattern lives once per block in shared memory, each warp keeps its own values), only the Cholesky
+// factor of K is dense (row-major, ld 33: conflict-free for both substitution sweeps).  The triangular solves run on
+// warp shuffles without any block barrier, so many QPs are in flight per SM.
+constexpr int kFastWarps = 4;  // QPs per thread block
+constexpr int kLdl = 33;
+
+struct FastDims {
+  int n, m, nnzP, nnzA, nnzPf;  // nnzPf: entries of the full symmetric pattern of P
+  long long stride;             // doubles of per-QP state in HBM
+  int oPv, oAv, oL, oInvd, oQ, oLo, oUp, oD, oE, oCt, oX, oZ, oY, oScal;
+  // shared pattern (shorts), offsets into the pattern array
+  int pAcp, pAri, pArp, pAcc, pAcq, pPrp, pPcc, pPcq, plen;
+};
+
+struct FastWarp {  // per-warp shared memory
+  double *Av, *Pv, *L, *invd, *vn0, *vn1, *vm0, *vm1;
+};
+
+__device__ __forceinline__ int fast_warp_doubles(const FastDims &d) {
+  return ((d.nnzA + 1) & ~1) + ((d.nnzP + 1) & ~1) + 32 * kLdl + 32 + 32 + 32 + 64 + 64 + 2;
+}
+size_t fast_smem_bytes(const FastDims &d) {
+  const int per = ((d.nnzA + 1) & ~1) + ((d.nnzP + 1) & ~1) + 32 * kLdl + 32 + 32 + 32 + 64 + 64 + 2;
+  return (size_t)kFastWarps * per * 8 + (((size_t)d.plen * 2 + 15) & ~(size_t)15) + 64;
+}
+__device__ __forceinline__ void fast_carve(FastWarp &W, const FastDims &d, double *base, int warp) {
+  double *p = base + (size_t)warp * fast_warp_doubles(d);
+  W.Av = p; p += (d.nnzA + 1) & ~1;
+  W.Pv = p; p += (d.nnzP + 1) & ~1;
+  W.L = p; p += 32 * kLdl;
+  W.invd = p; p += 32;
+  W.vn0 = p; p += 32;
+  W.vn1 = p; p += 32;
+  W.vm0 = p; p += 64;
+  W.vm1 = p;
+}
+
+__device__ __forceinline__ double wmax(double a) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+  return a;
+}
+__device__ __forceinline__ double wsum(double a) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  return a;
+}
+
+struct FastPat {  // the shared pattern in shared memory
+  const short *Acp, *Ari;            // A by columns (the caller's CSC): column pointers, row indices
+  const short *Arp, *Acc, *Acq;      // A by rows: row pointers, column indices, position in the CSC value array
+  const short *Prp, *Pcc, *Pcq;      // full symmetric P by rows: pointers, columns, position in the triu value array
+};
+__device__ __forceinline__ void fast_pat(FastPat &Q, const FastDims &d, const short *p) {
+  Q.Acp = p + d.pAcp; Q.Ari = p + d.pAri; Q.Arp = p + d.pArp; Q.Acc = p + d.pAcc; Q.Acq = p + d.pAcq;
+  Q.Prp = p + d.pPrp; Q.Pcc = p + d.pPcc; Q.Pcq = p + d.pPcq;
+}
+
+// row i of A times the n-vector in shared memory `v`
+__device__ __forceinline__ double arow(const FastPat &Q, const double *Av, const double *v, int i, int m) {
+  double a = 0.0;
+  if (i < m)
+    for (int k = Q.Arp[i]; k < Q.Arp[i + 1]; k++) a = fma(Av[Q.Acq[k]], v[Q.Acc[k]], a);
+  return a;
+}
+// column j of A times the m-vector in shared memory `v`  (= row j of A')
+__device__ __forceinline__ double acol(const FastPat &Q, const double *Av, const double *v, int j, int n) {
+  double a = 0.0;
+  if (j < n)
+    for (int k = Q.Acp[j]; k < Q.Acp[j + 1]; k++) a = fma(Av[k], v[Q.Ari[k]], a);
+  return a;
+}
+__device__ __forceinline__ double prow(const FastPat &Q, const double *Pv, const double *v, int j, int n) {
+  double a = 0.0;
+  if (j < n)
+    for (int k = Q.Prp[j]; k < Q.Prp[j + 1]; k++) a = fma(Pv[Q.Pcq[k]], v[Q.Pcc[k]], a);
+  return a;
+}
+
+// K = P + sigma I + A' diag(rho) A into W.L (row-major, lower triangle used), then Cholesky; lane j builds column j
+// of K on its own (no conflicts, fixed order).  rho of rows lane / lane + 32 in r0 / r1.  Returns false on a
+// non-positive pivot (uniform over the warp).
+__device__ bool fast_factor(const FastWarp &W, const FastPat &Q, const FastDims &d, double sigma, double r0, double r1) {
+  const int n = d.n, m = d.m, lane = threadIdx.x & 31;
+  if (lane < m) W.vm0[lane] = r0;
+  if (lane + 32 < m) W.vm0[lane + 32] = r1;
+  for (int e = lane; e < 32 * kLdl; e += 32) W.L[e] = 0.0;
+  __syncwarp();
+  if (lane < n) {
+    const int j = lane;
+    for (int k = Q.Prp[j]; k < Q.Prp[j + 1]; k++) W.L[Q.Pcc[k] * kLdl + j] += W.Pv[Q.Pcq[k]];  // K[c][j], column j
+    W.L[j * kLdl + j] += sigma;
+    for (int k = Q.Acp[j]; k < Q.Acp[j + 1]; k++) {
+      const int row = Q.Ari[k];
+      const double s = W.vm0[row] * W.Av[k];
+      for (int t = Q.Arp[row]; t < Q.Arp[row + 1]; t++) W.L[Q.Acc[t] * kLdl + j] += s * W.Av[Q.Acq[t]];
+    }
+  }
+  __syncwarp();
+  // right-looking Cholesky on the lower triangle: lane i owns row i
+  bool ok = true;
+  for (int k = 0; k < n; k++) {
+    const double dkk = W.L[k * kLdl + k];
+    if (!(dkk > 0.0)) { ok = false; break; }
+    const double r = sqrt(dkk), rinv = 1.0 / r;
+    __syncwarp();
+    double lik = 0.0;
+    if (lane == k) { W.L[k * kLdl + k] = r; W.invd[k] = rinv; }
+    if (lane > k && lane < n) { lik = W.L[lane * kLdl + k] * rinv; W.L[lane * kLdl + k] = lik; }
+    __syncwarp();
+    if (lane > k && lane < n)
+      for (int j = k + 1; j <= lane; j++) W.L[lane * kLdl + j] -= lik * W.L[j * kLdl + k];
+    __syncwarp();
+  }
+  // substitution form (fast_solve): strictly upper part zero, diagonal stored as L[k][k] - 1, rows >= n zero
+  if (ok && lane < n) {
+    for (int j = lane + 1; j < 32; j++) W.L[lane * kLdl + j] = 0.0;
+    W.L[lane * kLdl + lane] -= 1.0;
+  }
+  __syncwarp();
+  return ok;
+}
+
+// b (entry `lane` in a register) <- K^{-1} b by forward / backward substitution on warp shuffles.  `invd` is this
+// lane's 1 / L[lane][lane].  The factor is stored so that one branch-free update serves every lane: with
+// t = b_k / L_kk broadcast from lane k,  b <- b - M[lane][k] t  where M is L with zeros above the diagonal and
+// L_kk - 1 on it (lane k ends with b_k - (L_kk - 1) b_k / L_kk = b_k / L_kk, lanes above keep b).  The factor loads
+// do not depend on b, so the chain per column is one multiply, one shuffle and one fused multiply-add.
+__device__ __forceinline__ double fast_solve(const FastWarp &W, int n, double b, double invd) {
+  const int lane = threadIdx.x & 31;
+  const unsigned Ls = (unsigned)__cvta_generic_to_shared(W.L);
+  const unsigned Lrow = Ls + 8u * (unsigned)(lane * kLdl), Lcol = Ls + 8u * (unsigned)lane;
+#pragma unroll 6
+  for (int k = 0; k < n; k++) {
+    double lk;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lk) : "r"(Lrow + 8u * (unsigned)k));
+    const double t = __shfl_sync(0xffffffffu, b * invd, k);
+    b = fma(-lk, t, b);
+  }
+#pragma unroll 6
+  for (int k = n - 1; k >= 0; k--) {
+    double lk;  // M'[lane][k] = M[k][lane]
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lk) : "r"(Lcol + 8u * (unsigned)(k * kLdl)));
+    const double t = __shfl_sync(0xffffffffu, b * invd, k);
+    b = fma(-lk, t, b);
+  }
+  return b;
+}
+
+__device__ __forceinline__ int ctype_of(double l, double u) {
+  return (l < -kInfty * kMinScaling && u > kInfty * kMinScaling) ? -1 : (u - l < kRhoTol ? 1 : 0);
+}
+__device__ __forceinline__ double rho_of(int t, double rho) {
+  return t < 0 ? kRhoMin : (t == 1 ? kRhoEqOverIneq * rho : rho);
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps) batch_fast_setup_kernel(
+    FastDims d, long long count, double *state, const short *pattern, const double *Px, const double *Ax,
+    const double *q, const double *l, const double *u, int scaling_iters, double rho0, double sigma, int *fail) {
+  extern __shared__ __align__(16) double smem_b[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = d.n, m = d.m;
+  short *pat = reinterpret_cast<short *>(smem_b + (size_t)kFastWarps * fast_warp_doubles(d));
+  for (int e = threadIdx.x; e < d.plen; e += blockDim.x) pat[e] = pattern[e];
+  __syncthreads();
+  const long long b = (long long)blockIdx.x * kFastWarps + warp;
+  if (b >= count) return;
+  FastWarp W;
+  fast_carve(W, d, smem_b, warp);
+  FastPat Q;
+  fast_pat(Q, d, pat);
+  for (int k = lane; k < d.nnzA; k += 32) W.Av[k] = Ax[b * d.nnzA + k];
+  for (int k = lane; k < d.nnzP; k += 32) W.Pv[k] = Px[b * d.nnzP + k];
+  double qj = lane < n ? q[b * n + lane] : 0.0, Dj = 1.0;
+  double E0 = 1.0, E1 = 1.0, cost = 1.0;
+  __syncwarp();
+  for (int it = 0; it < scaling_iters; it++) {
+    // column norms of [P A'; A 0]: lane j -> column j (P is symmetric: row j of the full pattern), lanes -> rows of A
+    double cn = 0.0;
+    if (lane < n) {
+      for (int k = Q.Prp[lane]; k < Q.Prp[lane + 1]; k++) cn = fmax(cn, fabs(W.Pv[Q.Pcq[k]]));
+      for (int k = Q.Acp[lane]; k < Q.Acp[lane + 1]; k++) cn = fmax(cn, fabs(W.Av[k]));
+    }
+    double rn0 = 0.0, rn1 = 0.0;
+    if (lane < m) for (int k = Q.Arp[lane]; k < Q.Arp[lane + 1]; k++) rn0 = fmax(rn0, fabs(W.Av[Q.Acq[k]]));
+    if (lane + 32 < m) for (int k = Q.Arp[lane + 32]; k < Q.Arp[lane + 33]; k++) rn1 = fmax(rn1, fabs(W.Av[Q.Acq[k]]));
+    const double dt = 1.0 / sqrt(limit_scaling_b(cn)), e0 = 1.0 / sqrt(limit_scaling_b(rn0)), e1 = 1.0 / sqrt(limit_scaling_b(rn1));
+    if (lane < n) W.vn0[lane] = dt;
+    if (lane < m) W.vm0[lane] = e0;
+    if (lane + 32 < m) W.vm0[lane + 32] = e1;
+    __syncwarp();
+    // P <- Dt P Dt (smaller index first, as the single-QP engine), A <- Et A Dt: lane j scales column j of A and of triu(P)
+    if (lane < n) {
+      for (int k = Q.Acp[lane]; k < Q.Acp[lane + 1]; k++) W.Av[k] = (W.Av[k] * W.vm0[Q.Ari[k]]) * dt;
+    }
+    __syncwarp();
+    // triu(P) values: entry k of the triu array is reached through the full pattern rows with Pcc >= row (once)
+    if (lane < n)
+      for (int k = Q.Prp[lane]; k < Q.Prp[lane + 1]; k++) {
+        const int c = Q.Pcc[k];
+        if (c >= lane) W.Pv[Q.Pcq[k]] = (W.Pv[Q.Pcq[k]] * dt) * W.vn0[c];  // row = lane <= c
+      }
+    qj *= dt; Dj *= dt; E0 *= e0; E1 *= e1;
+    __syncwarp();
+    // cost normalisation
+    double pm = 0.0;
+    if (lane < n) for (int k = Q.Prp[lane]; k < Q.Prp[lane + 1]; k++) pm = fmax(pm, fabs(W.Pv[Q.Pcq[k]]));
+    const double mean = wsum(lane < n ? pm : 0.0) / (double)n, qn = wmax(lane < n ? fabs(qj) : 0.0);
+    const double ct = 1.0 / limit_scaling_b(fmax(mean, limit_scaling_b(qn)));
+    for (int k = lane; k < d.nnzP; k += 32) W.Pv[k] *= ct;
+    qj *= ct;
+    cost *= ct;
+    __syncwarp();
+  }
+  double l0 = lane < m ? E0 * l[b * m + lane] : 0.0, u0 = lane < m ? E0 * u[b * m + lane] : 0.0;
+  double l1 = lane + 32 < m ? E1 * l[b * m + lane + 32] : 0.0, u1 = lane + 32 < m ? E1 * u[b * m + lane + 32] : 0.0;
+  const int t0 = ctype_of(l0, u0), t1 = ctype_of(l1, u1);
+  const bool ok = fast_factor(W, Q, d, sigma, rho_of(t0, rho0), rho_of(t1, rho0));
+  if (!ok && lane == 0) atomicExch(fail, 1);
+  double *st = state + b * d.stride;
+  for (int k = lane; k < d.nnzA; k += 32) st[d.oAv + k] = W.Av[k];
+  for (int k = lane; k < d.nnzP; k += 32) st[d.oPv + k] = W.Pv[k];
+  for (int e = lane; e < 32 * kLdl; e += 32) st[d.oL + e] = W.L[e];
+  if (lane < n) { st[d.oInvd + lane] = W.invd[lane]; st[d.oQ + lane] = qj; st[d.oD + lane] = Dj; st[d.oX + lane] = 0.0; }
+  if (lane < m) { st[d.oLo + lane] = l0; st[d.oUp + lane] = u0; st[d.oE + lane] = E0; st[d.oCt + lane] = (double)t0; st[d.oZ + lane] = 0.0; st[d.oY + lane] = 0.0; }
+  if (lane + 32 < m) {
+    const int i = lane + 32;
+    st[d.oLo + i] = l1; st[d.oUp + i] = u1; st[d.oE + i] = E1; st[d.oCt + i] = (double)t1; st[d.oZ + i] = 0.0; st[d.oY + i] = 0.0;
+  }
+  if (lane == 0) { st[d.oScal] = cost; st[d.oScal + 1] = rho0; st[d.oScal + 2] = 0.0; }
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps) batch_fast_update_kernel(
+    FastDims d, long long count, double *state, const short *pattern, const double *q, const double *l, const double *u,
+    const double *x, const double *y, int scaling) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = d.n, m = d.m;
+  const long long b = (long long)blockIdx.x * kFastWarps + warp;
+  if (b >= count) return;
+  double *st = state + b * d.stride;
+  const double c = st[d.oScal];
+  if (q && lane < n) st[d.oQ + lane] = (q[b * n + lane] * st[d.oD + lane]) * c;
+  for (int i = lane; i < m; i += 32) {
+    if (l) st[d.oLo + i] = st[d.oE + i] * l[b * m + i];
+    if (u) st[d.oUp + i] = st[d.oE + i] * u[b * m + i];
+    if (y) st[d.oY + i] = scaling ? (y[b * m + i] / st[d.oE + i]) * c : y[b * m + i];
+  }
+  if (x) {
+    if (lane < n) st[d.oX + lane] = scaling ? x[b * n + lane] / st[d.oD + lane] : x[b * n + lane];
+    __syncwarp();
+    const short *Arp = pattern + d.pArp, *Acc = pattern + d.pAcc, *Acq = pattern + d.pAcq;
+    for (int i = lane; i < m; i += 32) {
+      double a = 0.0;
+      for (int k = Arp[i]; k < Arp[i + 1]; k++) a = fma(st[d.oAv + Acq[k]], st[d.oX + Acc[k]], a);
+      st[d.oZ + i] = a;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
+    FastDims d, long long count, double *state, const short *pattern, SolveCfg c, long long adaptive_interval,
+    int bounds_changed, double *x_out, double *y_out, OSQPB200BatchInfo *info_out) {
+  extern __shared__ __align__(16) double smem_b[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = d.n, m = d.m;
+  short *pat = reinterpret_cast<short *>(smem_b + (size_t)kFastWarps * fast_warp_doubles(d));
+  for (int e = threadIdx.x; e < d.plen; e += blockDim.x) pat[e] = pattern[e];
+  __syncthreads();
+  const long long b = (long long)blockIdx.x * kFastWarps + warp;
+  if (b >= count) return;
+  FastWarp W;
+  fast_carve(W, d, smem_b, warp);
+  FastPat Q;
+  fast_pat(Q, d, pat);
+  double *st = state + b * d.stride;
+  for (int k = lane; k < d.nnzA; k += 32) W.Av[k] = st[d.oAv + k];
+  for (int k = lane; k < d.nnzP; k += 32) W.Pv[k] = st[d.oPv + k];
+  for (int e = lane; e < 32 * kLdl; e += 32) W.L[e] = st[d.oL + e];
+  const bool hn = lane < n, h0 = lane < m, h1 = lane + 32 < m;
+  const int i1 = lane + 32;
+  if (hn) W.invd[lane] = st[d.oInvd + lane];
+  const double qj = hn ? st[d.oQ + lane] : 0.0, Dj = hn ? st[d.oD + lane] : 1.0, Dinv = 1.0 / Dj;
+  double x = (hn && c.warm_start) ? st[d.oX + lane] : 0.0, dx = 0.0;
+  const double l0 = h0 ? st[d.oLo + lane] : 0.0, u0 = h0 ? st[d.oUp + lane] : 0.0, E0 = h0 ? st[d.oE + lane] : 1.0;
+  const double l1 = h1 ? st[d.oLo + i1] : 0.0, u1 = h1 ? st[d.oUp + i1] : 0.0, E1 = h1 ? st[d.oE + i1] : 1.0;
+  const double Ei0 = 1.0 / E0, Ei1 = 1.0 / E1;
+  int t0 = h0 ? (int)st[d.oCt + lane] : 0, t1 = h1 ? (int)st[d.oCt + i1] : 0;
+  double z0 = (h0 && c.warm_start) ? st[d.oZ + lane] : 0.0, z1 = (h1 && c.warm_start) ? st[d.oZ + i1] : 0.0;
+  double y0 = (h0 && c.warm_start) ? st[d.oY + lane] : 0.0, y1 = (h1 && c.warm_start) ? st[d.oY + i1] : 0.0;
+  double dy0 = 0.0, dy1 = 0.0;
+  const double cost_c = st[d.oScal], cost_cinv = 1.0 / cost_c;
+  double rho = st[d.oScal + 1];
+  long long rho_updates = (long long)st[d.oScal + 2];
+  __syncwarp();
+  bool refactor = false;
+  if (bounds_changed) {
+    int ch = 0;
+    if (h0) { const int t = ctype_of(l0, u0); if (t != t0) { t0 = t; ch = 1; } }
+    if (h1) { const int t = ctype_of(l1, u1); if (t != t1) { t1 = t; ch = 1; } }
+    refactor = __any_sync(0xffffffffu, ch);
+  }
+  double r0 = rho_of(t0, rho), r1 = rho_of(t1, rho), ri0 = 1.0 / r0, ri1 = 1.0 / r1;
+  long long status = ST_UNSOLVED;
+  if (refactor && !fast_factor(W, Q, d, c.sigma, r0, r1)) status = ST_NON_CVX;
+  __syncwarp();
+  double invd_lane = hn ? W.invd[lane] : 0.0;
+  const bool unscale = c.scaling && !c.scaled_termination;
+
+  InfoScalars I;
+  I.pri_res = I.dua_res = I.obj_val = 0.0;
+  I.ndx_t = I.ndy_t = 1.0;
+  auto info = [&]() {
+    // x, dx -> vn0, vn1 ; y, dy -> vm0, vm1
+    if (hn) { W.vn0[lane] = x; W.vn1[lane] = dx; }
+    if (h0) { W.vm0[lane] = y0; W.vm1[lane] = dy0; }
+    if (h1) { W.vm0[i1] = y1; W.vm1[i1] = dy1; }
+    __syncwarp();
+    const double Ax0 = arow(Q, W.Av, W.vn0, lane, m), Ax1 = arow(Q, W.Av, W.vn0, i1, m);
+    const double Adx0 = arow(Q, W.Av, W.vn1, lane, m), Adx1 = arow(Q, W.Av, W.vn1, i1, m);
+    const double Px = prow(Q, W.Pv, W.vn0, lane, n), Pdx = prow(Q, W.Pv, W.vn1, lane, n);
+    const double Aty = acol(Q, W.Av, W.vm0, lane, n), Atdy = acol(Q, W.Av, W.vm1, lane, n);
+    const double e0 = unscale ? Ei0 : 1.0, e1 = unscale ? Ei1 : 1.0, EE0 = unscale ? E0 : 1.0, EE1 = unscale ? E1 : 1.0;
+    const double pr0 = h0 ? fabs(Ax0 - z0) : 0.0, pr1 = h1 ? fabs(Ax1 - z1) : 0.0;
+    I.pri_t = wmax(fmax(e0 * pr0, e1 * pr1));
+    I.pri_r = wmax(fmax(pr0, pr1));
+    I.nz_t = wmax(fmax(h0 ? e0 * fabs(z0) : 0.0, h1 ? e1 * fabs(z1) : 0.0));
+    I.nz_r = wmax(fmax(h0 ? fabs(z0) : 0.0, h1 ? fabs(z1) : 0.0));
+    I.nAx_t = wmax(fmax(h0 ? e0 * fabs(Ax0) : 0.0, h1 ? e1 * fabs(Ax1) : 0.0));
+    I.nAx_r = wmax(fmax(h0 ? fabs(Ax0) : 0.0, h1 ? fabs(Ax1) : 0.0));
+    I.ndy_t = wmax(fmax(h0 ? EE0 * fabs(dy0) : 0.0, h1 ? EE1 * fabs(dy1) : 0.0));
+    I.lhs = wsum((h0 ? u0 * fmax(dy0, 0.0) + l0 * fmin(dy0, 0.0) : 0.0) + (h1 ? u1 * fmax(dy1, 0.0) + l1 * fmin(dy1, 0.0) : 0.0));
+    double mu = -INFINITY, ml = -INFINITY;
+    if (h0) { if (u0 < kInfty * kMinScaling) mu = fmax(mu, e0 * Adx0); if (l0 > -kInfty * kMinScaling) ml = fmax(ml, -e0 * Adx0); }
+    if (h1) { if (u1 < kInfty * kMinScaling) mu = fmax(mu, e1 * Adx1); if (l1 > -kInfty * kMinScaling) ml = fmax(ml, -e1 * Adx1); }
+    I.maxU_t = wmax(mu);
+    I.maxNegL_t = wmax(ml);
+    const double di = unscale ? Dinv : 1.0, DD = unscale ? Dj : 1.0;
+    const double dr = hn ? fabs(qj + Px + Aty) : 0.0;
+    I.dua_t = wmax(di * dr); I.dua_r = wmax(dr);
+    I.nq_t = wmax(hn ? di * fabs(qj) : 0.0); I.nq_r = wmax(hn ? fabs(qj) : 0.0);
+    I.nAty_t = wmax(hn ? di * fabs(Aty) : 0.0); I.nAty_r = wmax(hn ? fabs(Aty) : 0.0);
+    I.nPx_t = wmax(hn ? di * fabs(Px) : 0.0); I.nPx_r = wmax(hn ? fabs(Px) : 0.0);
+    I.obj = wsum(hn ? x * (0.5 * Px + qj) : 0.0);
+    I.ndx_t = wmax(hn ? DD * fabs(dx) : 0.0);
+    I.qdx = wsum(hn ? qj * dx : 0.0);
+    I.nPdx_t = wmax(hn ? di * fabs(Pdx) : 0.0);
+    I.nAtdy_t = wmax(hn ? di * fabs(Atdy) : 0.0);
+    I.obj_val = c.scaling ? I.obj * cost_cinv : I.obj;
+    I.pri_res = (m == 0) ? 0.0 : I.pri_t;
+    I.dua_res = unscale ? cost_cinv * I.dua_t : I.dua_t;
+    __syncwarp();
+  };
+
+  long long it = 0, info_iter = 0;
+  double rho_est = rho;
+  bool checked = false;
+  if (status == ST_UNSOLVED)
+    for (it = 1; it <= c.max_iter; it++) {
+      // rhs = sigma x - q + A'(rho z - y)
+      if (h0) W.vm0[lane] = r0 * z0 - y0;
+      if (h1) W.vm0[i1] = r1 * z1 - y1;
+      __syncwarp();
+      double bj = hn ? c.sigma * x - qj + acol(Q, W.Av, W.vm0, lane, n) : 0.0;
+      const double xt = fast_solve(W, n, bj, invd_lane);
+      if (hn) W.vn0[lane] = xt;
+      __syncwarp();
+      const double zt0 = arow(Q, W.Av, W.vn0, lane, m), zt1 = arow(Q, W.Av, W.vn0, i1, m);
+      __syncwarp();
+      if (hn) { const double xn = c.alpha * xt + (1.0 - c.alpha) * x; dx = xn - x; x = xn; }
+      if (h0) {
+        const double zh = c.alpha * zt0 + (1.0 - c.alpha) * z0;
+        const double zn = fmin(fmax(zh + ri0 * y0, l0), u0);
+        double dd = r0 * (zh - zn);
+        y0 += dd; z0 = zn;
+        if (u0 > kInfty * kMinScaling) dd = (l0 < -kInfty * kMinScaling) ? 0.0 : fmin(dd, 0.0);
+        else if (l0 < -kInfty * kMinScaling) dd = fmax(dd, 0.0);
+        dy0 = dd;
+      }
+      if (h1) {
+        const double zh = c.alpha * zt1 + (1.0 - c.alpha) * z1;
+        const double zn = fmin(fmax(zh + ri1 * y1, l1), u1);
+        double dd = r1 * (zh - zn);
+        y1 += dd; z1 = zn;
+        if (u1 > kInfty * kMinScaling) dd = (l1 < -kInfty * kMinScaling) ? 0.0 : fmin(dd, 0.0);
+        else if (l1 < -kInfty * kMinScaling) dd = fmax(dd, 0.0);
+        dy1 = dd;
+      }
+      checked = c.check_termination && (it % c.check_termination == 0);
+      const bool adapt = c.adaptive_rho && adaptive_interval && (it % adaptive_interval == 0);
+      if (checked || adapt) {
+        info();
+        info_iter = it;
+        if (checked) {
+          status = check_termination(I, c, m, cost_c, cost_cinv, false);
+          if (status != ST_UNSOLVED) break;
+        }
+      }
+      if (adapt) {
+        const double rho_new = rho_estimate(I, rho);
+        rho_est = rho_new;
+        if (rho_new > rho * c.adaptive_rho_tolerance || rho_new < rho / c.adaptive_rho_tolerance) {
+          rho = fmin(fmax(rho_new, kRhoMin), kRhoMax);
+          rho_updates++;
+          r0 = rho_of(t0, rho); r1 = rho_of(t1, rho); ri0 = 1.0 / r0; ri1 = 1.0 / r1;
+          if (!fast_factor(W, Q, d, c.sigma, r0, r1)) { status = ST_NON_CVX; break; }
+          __syncwarp();
+          invd_lane = hn ? W.invd[lane] : 0.0;
+          refactor = true;
+        }
+      }
+    }
+  if (status == ST_UNSOLVED) {
+    if (!checked) {
+      info();
+      info_iter = it - 1;
+      status = check_termination(I, c, m, cost_c, cost_cinv, false);
+    }
+    if (status == ST_UNSOLVED) {
+      const long long s2 = check_termination(I, c, m, cost_c, cost_cinv, true);
+      status = (s2 != ST_UNSOLVED) ? s2 : ST_MAX_ITER;
+    }
+  }
+  if (status != ST_NON_CVX) rho_est = rho_estimate(I, rho);
+  double obj_val = I.obj_val;
+  if (status == ST_NON_CVX) obj_val = nan("");
+  const bool pinf = (status == ST_PINF || status == ST_PINF_INACC), dinf = (status == ST_DINF || status == ST_DINF_INACC);
+  if (pinf) obj_val = kInfty;
+  if (dinf) obj_val = -kInfty;
+  const bool has_sol = !(pinf || dinf || status == ST_NON_CVX);
+  if (hn) {
+    double out;
+    if (has_sol) out = c.scaling ? Dj * x : x;
+    else if (dinf) out = (unscale ? Dj : 1.0) * dx / I.ndx_t;
+    else out = nan("");
+    x_out[b * n + lane] = out;
+    st[d.oX + lane] = has_sol ? x : 0.0;
+  }
+  if (h0) {
+    double out;
+    if (has_sol) out = c.scaling ? cost_cinv * E0 * y0 : y0;
+    else if (pinf) out = (unscale ? E0 : 1.0) * dy0 / I.ndy_t;
+    else out = nan("");
+    y_out[b * m + lane] = out;
+    st[d.oZ + lane] = has_sol ? z0 : 0.0; st[d.oY + lane] = has_sol ? y0 : 0.0; st[d.oCt + lane] = (double)t0;
+  }
+  if (h1) {
+    double out;
+    if (has_sol) out = c.scaling ? cost_cinv * E1 * y1 : y1;
+    else if (pinf) out = (unscale ? E1 : 1.0) * dy1 / I.ndy_t;
+    else out = nan("");
+    y_out[b * m + i1] = out;
+    st[d.oZ + i1] = has_sol ? z1 : 0.0; st[d.oY + i1] = has_sol ? y1 : 0.0; st[d.oCt + i1] = (double)t1;
+  }
+  if (refactor) {
+    __syncwarp();
+    for (int e = lane; e < 32 * kLdl; e += 32) st[d.oL + e] = W.L[e];
+    if (hn) st[d.oInvd + lane] = W.invd[lane];
+  }
+  if (lane == 0) {
+    st[d.oScal + 1] = rho;
+    st[d.oScal + 2] = (double)rho_updates;
+    OSQPB200BatchInfo &o = info_out[b];
+    o.iter = info_iter; o.status_val = status; o.obj_val = obj_val; o.pri_res = I.pri_res; o.dua_res = I.dua_res;
+    o.rho_estimate = rho_est; o.rho_updates = rho_updates;
+  }
+}
+
 double now_s() {
   using namespace std::chrono;
   return duration<double>(steady_clock::now().time_since_epoch()).count();
@@ -521,6 +987,10 @@ struct OSQPB200Batch {
   int block = 64;
   int bounds_changed = 0;
   double setup_time = 0, solve_ms = 0;
+  // fast path (one warp per QP)
+  bool fast = false;
+  FastDims f{};
+  short *d_pattern = nullptr;
 };
 
 namespace {
@@ -556,7 +1026,7 @@ void free_batch(OSQPB200Batch *b) {
   DevGuard g(b->device);
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->state); cudaFree(b->Pp); cudaFree(b->Pi); cudaFree(b->Ap); cudaFree(b->Ai);
-  cudaFree(b->stage); cudaFree(b->d_info); cudaFree(b->d_fail);
+  cudaFree(b->stage); cudaFree(b->d_info); cudaFree(b->d_fail); cudaFree(b->d_pattern);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -634,6 +1104,71 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
   b->block = std::min(256, std::max(64, ((int)std::max(n, m) + 31) & ~31));
   cudaDeviceProp prop;
   BCU(cudaGetDeviceProperties(&prop, b->device));
+  // ---- fast path: one warp per QP with the sparse pattern (n <= 32, m <= 64)
+  {
+    const char *envf = getenv("OSQP_B200_BATCH_FAST");
+    std::vector<short> pat;
+    FastDims &f = b->f;
+    if (n <= 32 && m <= 64 && nnzA <= 30000 && nnzP <= 15000 && !(envf && atoi(envf) == 0)) {
+      f.n = (int)n; f.m = (int)m; f.nnzP = (int)nnzP; f.nnzA = (int)nnzA;
+      // A by rows
+      std::vector<short> Arp(m + 1, 0), Acc(nnzA), Acq(nnzA);
+      for (c_int k = 0; k < nnzA; k++) Arp[pattern->A->i[k] + 1]++;
+      for (c_int i = 0; i < m; i++) Arp[i + 1] += Arp[i];
+      {
+        std::vector<short> w(Arp.begin(), Arp.end() - 1);
+        for (c_int j = 0; j < n; j++)
+          for (c_int k = pattern->A->p[j]; k < pattern->A->p[j + 1]; k++) {
+            const short pos = w[pattern->A->i[k]]++;
+            Acc[pos] = (short)j;
+            Acq[pos] = (short)k;
+          }
+      }
+      // full symmetric P by rows
+      std::vector<short> Prp(n + 1, 0);
+      for (c_int j = 0; j < n; j++)
+        for (c_int k = pattern->P->p[j]; k < pattern->P->p[j + 1]; k++) {
+          const c_int i = pattern->P->i[k];
+          Prp[i + 1]++;
+          if (i != j) Prp[j + 1]++;
+        }
+      for (c_int i = 0; i < n; i++) Prp[i + 1] += Prp[i];
+      f.nnzPf = Prp[n];
+      std::vector<short> Pcc(std::max(1, f.nnzPf)), Pcq(std::max(1, f.nnzPf));
+      {
+        std::vector<short> w(Prp.begin(), Prp.end() - 1);
+        for (c_int j = 0; j < n; j++)
+          for (c_int k = pattern->P->p[j]; k < pattern->P->p[j + 1]; k++) {
+            const c_int i = pattern->P->i[k];
+            short pos = w[i]++;
+            Pcc[pos] = (short)j; Pcq[pos] = (short)k;
+            if (i != j) { pos = w[j]++; Pcc[pos] = (short)i; Pcq[pos] = (short)k; }
+          }
+      }
+      auto put = [&](const std::vector<short> &v) { int o = (int)pat.size(); pat.insert(pat.end(), v.begin(), v.end()); return o; };
+      std::vector<short> Acp(n + 1), Ari(std::max<c_int>(1, nnzA));
+      for (c_int j = 0; j <= n; j++) Acp[j] = (short)pattern->A->p[j];
+      for (c_int k = 0; k < nnzA; k++) Ari[k] = (short)pattern->A->i[k];
+      f.pAcp = put(Acp); f.pAri = put(Ari); f.pArp = put(Arp); f.pAcc = put(Acc); f.pAcq = put(Acq);
+      f.pPrp = put(Prp); f.pPcc = put(Pcc); f.pPcq = put(Pcq);
+      f.plen = (int)pat.size();
+      int o = 0;
+      auto take = [&](int k) { int r = o; o += (k + 1) & ~1; return r; };
+      f.oPv = take(f.nnzP); f.oAv = take(f.nnzA); f.oL = take(32 * kLdl); f.oInvd = take(f.n); f.oQ = take(f.n);
+      f.oLo = take(f.m); f.oUp = take(f.m); f.oD = take(f.n); f.oE = take(f.m); f.oCt = take(f.m); f.oX = take(f.n);
+      f.oZ = take(f.m); f.oY = take(f.m); f.oScal = take(4);
+      f.stride = o;
+      b->fast = fast_smem_bytes(f) <= (size_t)prop.sharedMemPerBlockOptin;
+    }
+    if (b->fast) {
+      b->smem = fast_smem_bytes(f);
+      BCU(cudaFuncSetAttribute(batch_fast_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+      BCU(cudaFuncSetAttribute(batch_fast_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+      BCU(cudaMalloc(&b->d_pattern, pat.size() * sizeof(short)));
+      BCU(cudaMemcpy(b->d_pattern, pat.data(), pat.size() * sizeof(short), cudaMemcpyHostToDevice));
+      d.stride = f.stride;  // the state allocation below uses the fast layout
+    }
+  }
   if (b->smem > (size_t)prop.sharedMemPerBlockOptin) {
     fprintf(stderr, "ERROR in osqp_batch_setup: a QP of this size (%zu B) does not fit in shared memory\n", b->smem);
     return 1;
@@ -668,9 +1203,14 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
   }
   const double rho0 = std::min(std::max(settings->rho, 1e-6), 1e6);
   b->st.rho = rho0;
-  batch_setup_kernel<<<(unsigned)count, b->block, b->smem, b->stream>>>(d, b->state, b->Pp, b->Pi, b->Ap, b->Ai, dPx,
-                                                                        dAx, dq, dl, du, (int)settings->scaling, rho0,
-                                                                        settings->sigma, b->d_fail);
+  if (b->fast)
+    batch_fast_setup_kernel<<<(unsigned)((count + kFastWarps - 1) / kFastWarps), 32 * kFastWarps, b->smem, b->stream>>>(
+        b->f, count, b->state, b->d_pattern, dPx, dAx, dq, dl, du, (int)settings->scaling, rho0, settings->sigma,
+        b->d_fail);
+  else
+    batch_setup_kernel<<<(unsigned)count, b->block, b->smem, b->stream>>>(d, b->state, b->Pp, b->Pi, b->Ap, b->Ai, dPx,
+                                                                          dAx, dq, dl, du, (int)settings->scaling, rho0,
+                                                                          settings->sigma, b->d_fail);
   BCU(cudaGetLastError());
   int failed = 0;
   BCU(cudaMemcpyAsync(&failed, b->d_fail, sizeof(int), cudaMemcpyDeviceToHost, b->stream));
@@ -696,9 +1236,14 @@ c_int osqp_batch_update(OSQPB200Batch *b, const c_float *q, const c_float *l, co
   if (q) BCU(cudaMemcpyAsync(dq, q, (size_t)count * n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
   if (l && m > 0) BCU(cudaMemcpyAsync(dl, l, (size_t)count * m * sizeof(double), cudaMemcpyHostToDevice, b->stream));
   if (u && m > 0) BCU(cudaMemcpyAsync(du, u, (size_t)count * m * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-  batch_update_kernel<<<(unsigned)count, b->block, 8 * (n + 2), b->stream>>>(b->d, b->state, q ? dq : nullptr,
-                                                                           l ? dl : nullptr, u ? du : nullptr, nullptr,
-                                                                           nullptr, b->st.scaling != 0);
+  if (b->fast)
+    batch_fast_update_kernel<<<(unsigned)((count + kFastWarps - 1) / kFastWarps), 32 * kFastWarps, 0, b->stream>>>(
+        b->f, count, b->state, b->d_pattern, q ? dq : nullptr, l ? dl : nullptr, u ? du : nullptr, nullptr, nullptr,
+        b->st.scaling != 0);
+  else
+    batch_update_kernel<<<(unsigned)count, b->block, 8 * (n + 2), b->stream>>>(b->d, b->state, q ? dq : nullptr,
+                                                                             l ? dl : nullptr, u ? du : nullptr, nullptr,
+                                                                             nullptr, b->st.scaling != 0);
   BCU(cudaGetLastError());
   BCU(cudaStreamSynchronize(b->stream));  // the inputs are caller-owned
   if (l || u) b->bounds_changed = 1;
@@ -712,9 +1257,14 @@ c_int osqp_batch_warm_start(OSQPB200Batch *b, const c_float *x, const c_float *y
   double *dx = b->stage, *dy = dx + (size_t)count * n;
   if (x) BCU(cudaMemcpyAsync(dx, x, (size_t)count * n * sizeof(double), cudaMemcpyHostToDevice, b->stream));
   if (y && m > 0) BCU(cudaMemcpyAsync(dy, y, (size_t)count * m * sizeof(double), cudaMemcpyHostToDevice, b->stream));
-  batch_update_kernel<<<(unsigned)count, b->block, 8 * (n + 2), b->stream>>>(b->d, b->state, nullptr, nullptr, nullptr,
-                                                                           x ? dx : nullptr, (y && m > 0) ? dy : nullptr,
-                                                                           b->st.scaling != 0);
+  if (b->fast)
+    batch_fast_update_kernel<<<(unsigned)((count + kFastWarps - 1) / kFastWarps), 32 * kFastWarps, 0, b->stream>>>(
+        b->f, count, b->state, b->d_pattern, nullptr, nullptr, nullptr, x ? dx : nullptr, (y && m > 0) ? dy : nullptr,
+        b->st.scaling != 0);
+  else
+    batch_update_kernel<<<(unsigned)count, b->block, 8 * (n + 2), b->stream>>>(b->d, b->state, nullptr, nullptr, nullptr,
+                                                                             x ? dx : nullptr, (y && m > 0) ? dy : nullptr,
+                                                                             b->st.scaling != 0);
   BCU(cudaGetLastError());
   BCU(cudaStreamSynchronize(b->stream));
   b->st.warm_start = 1;
@@ -730,8 +1280,12 @@ c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB20
   if (b->st.adaptive_rho && interval == 0) interval = 50;  // no wall-clock rule inside a batch
   double *dx = b->stage, *dy = dx + (size_t)count * n;
   BCU(cudaEventRecord(b->ev0, b->stream));
-  batch_solve_kernel<<<(unsigned)count, b->block, b->smem, b->stream>>>(b->d, b->state, c, interval, b->bounds_changed,
-                                                                        dx, dy, b->d_info);
+  if (b->fast)
+    batch_fast_solve_kernel<<<(unsigned)((count + kFastWarps - 1) / kFastWarps), 32 * kFastWarps, b->smem, b->stream>>>(
+        b->f, count, b->state, b->d_pattern, c, interval, b->bounds_changed, dx, dy, b->d_info);
+  else
+    batch_solve_kernel<<<(unsigned)count, b->block, b->smem, b->stream>>>(b->d, b->state, c, interval, b->bounds_changed,
+                                                                          dx, dy, b->d_info);
   BCU(cudaGetLastError());
   BCU(cudaEventRecord(b->ev1, b->stream));
   BCU(cudaMemcpyAsync(x_out, dx, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
