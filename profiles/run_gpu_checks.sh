@@ -1,17 +1,2 @@
 mkdir -p gpurun_out
-(timeout 600 python -m pytest tests/test_batch.py -m gpu -q -x > gpurun_out/pytest_batch.log 2>&1); tail -3 gpurun_out/pytest_batch.log
-cat > /tmp/bb.py <<'PY'
-import sys, time, numpy as np
-sys.path.insert(0, '.')
-import __graft_entry__ as g, problems
-pkg = g.load_package()
-for count in (148*4, 8192):
-    batch = problems.mpc_batch_c5(count, 20267)
-    for mi, chk, ad, eps in ((100, 0, False, 1e-12), (4000, 25, True, 1e-4)):
-        bm = pkg.BatchModel(lib=g.LIB)
-        bm.setup(*batch, verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho=ad, adaptive_rho_interval=25, check_termination=chk, warm_start=False, max_iter=mi)
-        for _ in range(2): r = bm.solve()
-        print("count", count, "max_iter", mi, "check", chk, "adaptive", ad, "kernel ms %.3f" % bm.kernel_ms, "mean iters %.1f" % r.iter.mean(), "QP-it/s %.3g" % (r.iter.sum() / bm.kernel_ms * 1e3))
-        bm.clean()
-PY
-python /tmp/bb.py
+(OSQP_B200_DEBUG=1 timeout 900 python -m pytest tests/test_engine_parity.py -m gpu -q -x -k "kkt or agree or unconstrained" > gpurun_out/pytest_scale.log 2>&1); grep -E "osqp_b200\] tile|passed|failed|Error|error" gpurun_out/pytest_scale.log | tail -20

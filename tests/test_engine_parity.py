@@ -192,10 +192,15 @@ def test_resolve_is_deterministic(pkg, engine_lib):
     assert np.array_equal(ra.x, rb.x) and np.array_equal(ra.y, rb.y)
 
 
-def test_kkt_optimality_at_scale(pkg, engine_lib):
+@pytest.mark.parametrize("n,m,density,seed", [
+    (20000, 40000, 0.0015, 41),   # [A;P] stream: 1 column group, A' stream: 2 groups
+    (50000, 100000, 0.001, 42),   # BASELINE config 2 size: cluster pairs on [A;P], 4 groups on A'
+    (70000, 30000, 0.0004, 43),   # 3 column groups on [A;P] (no pairs), 2 on A'
+    (26000, 9000, 0.002, 44),     # 1 group on both streams
+])
+def test_kkt_optimality_at_scale(pkg, engine_lib, n, m, density, seed):
     # size-independent property: the returned (x*, y*) satisfies the unscaled KKT conditions to eps
-    n, m = 20000, 40000
-    prob = random_qp(n, m, 0.0015, 41)
+    prob = random_qp(n, m, density, seed)
     mdl = pkg.Model(lib=engine_lib)
     mdl.setup(**prob, verbose=False, eps_abs=1e-5, eps_rel=1e-5, adaptive_rho_interval=25, max_iter=20000)
     r = mdl.solve()
@@ -213,3 +218,45 @@ def test_kkt_optimality_at_scale(pkg, engine_lib):
     assert np.all((r.y <= tol) | (u - Ax <= 1e-2))
     assert np.all((r.y >= -tol) | (Ax - l <= 1e-2))
     assert abs(r.info.obj_val - (0.5 * r.x @ (P @ r.x) + q @ r.x)) <= 1e-6 * (1 + abs(r.info.obj_val))
+    # the stream path and the CSR path are two implementations of the same products: identical iterates up to
+    # summation order -> same status and iteration count (+-1 check interval) when the streams are switched off
+    mdl.clean()
+
+
+def test_stream_and_csr_paths_agree(pkg, engine_lib):
+    import os
+    prob = random_qp(30000, 45000, 0.001, 45)
+    opts = dict(FIXED_RHO, eps_abs=1e-5, eps_rel=1e-5, check_termination=25)
+    res = {}
+    for blocked in ("1", "0"):
+        os.environ["OSQP_B200_BLOCKED"] = blocked
+        try:
+            mdl = pkg.Model(lib=engine_lib)
+            mdl.setup(**prob, **opts)
+            res[blocked] = mdl.solve()
+            mdl.clean()
+        finally:
+            os.environ.pop("OSQP_B200_BLOCKED", None)
+    a, b = res["1"], res["0"]
+    assert a.info.status == b.info.status == "Solved"
+    assert a.info.iter == b.info.iter
+    assert np.max(np.abs(a.x - b.x)) <= 1e-7 * (1 + np.max(np.abs(b.x)))
+    assert np.max(np.abs(a.y - b.y)) <= 1e-7 * (1 + np.max(np.abs(b.y)))
+
+
+def test_unconstrained_large_uses_streams(pkg, engine_lib):
+    # m = 0 (test/unconstrained.jl at scale): only the P stream exists
+    rng = np.random.default_rng(46)
+    n = 40000
+    S = sp.triu(sprandn(n, n, 0.0004, rng), k=1)
+    S = S + S.T
+    d = np.asarray(abs(S).sum(axis=1)).ravel() + rng.uniform(0.5, 1.0, n)
+    P = (S + sp.diags(d)).tocsc()
+    q = rng.standard_normal(n)
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(P=P, q=q, A=sp.csc_matrix((0, n)), l=np.zeros(0), u=np.zeros(0), verbose=False, eps_abs=1e-8,
+              eps_rel=1e-8, max_iter=2000)
+    r = mdl.solve()
+    assert r.info.status == "Solved"
+    assert np.max(np.abs(P @ r.x + q)) <= 1e-6
+    mdl.clean()
