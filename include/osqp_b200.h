@@ -37,6 +37,10 @@ typedef struct {
    * rhs vector, barriers | 9 stream A' rhs + barrier | 10 rhs/residual + reduce | 11 residual refresh (CSR path) |
    * 12 update_info (CSR path) | 13 rho update | 14 epilogue | 15 unused */
   c_float phase_us[16];
+  c_int   streams;       /* 1: the hot phases run on tile streams; 0: CSR path (small / declined problems) */
+  c_int   groups_A;      /* column groups of the [A; P] stream and of the A' stream */
+  c_int   groups_At;
+  c_int   paired;        /* 1: [A; P] stream runs as cluster pairs with the DSMEM combine */
 } OSQPB200Profile;
 
 /* Measurement of the last osqp_solve on this workspace. */

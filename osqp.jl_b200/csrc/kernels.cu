@@ -1536,12 +1536,17 @@ __global__ void k_ruiz_apply(const DevPtrs d) {
   }
 }
 
-// cost normalisation: c_temp = 1 / limit(max(mean_j |P_:j|inf, limit(|q|inf)))   (single block)
-__global__ void __launch_bounds__(1024) k_ruiz_cost(const DevPtrs d) {
-  __shared__ double ssum[32], smax[32];
+// cost normalisation: c_temp = 1 / limit(max(mean_j |P_:j|inf, limit(|q|inf))).  Two fixed-order stages (the value
+// must be bit-identical from run to run): every block reduces a contiguous slice of the columns into red[], one
+// block combines the per-block values.
+constexpr int kCostBlocks = 148;
+__global__ void __launch_bounds__(256) k_ruiz_cost_partial(const DevPtrs d) {
+  __shared__ double ssum[8], smax[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int per = (d.n + gridDim.x - 1) / gridDim.x;
+  const int r0 = blockIdx.x * per, r1 = min(d.n, r0 + per);
   double sum = 0.0, qmax = 0.0;
-  for (int r = warp; r < d.n; r += nwarps) {
+  for (int r = r0 + warp; r < r1; r += nwarps) {
     double mx = 0.0;
     for (int k = d.P.rowptr[r] + lane; k < d.P.rowptr[r + 1]; k += 32) mx = fmax(mx, fabs(d.P.val[k]));
     for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -1552,6 +1557,14 @@ __global__ void __launch_bounds__(1024) k_ruiz_cost(const DevPtrs d) {
   if (threadIdx.x == 0) {
     double s = 0.0, q = 0.0;
     for (int w = 0; w < nwarps; w++) { s += ssum[w]; q = fmax(q, smax[w]); }
+    d.red[blockIdx.x] = s;               // d.red is free outside the cooperative kernels
+    d.red[kCostBlocks + blockIdx.x] = q;
+  }
+}
+__global__ void k_ruiz_cost(const DevPtrs d, int nblocks) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0, q = 0.0;
+    for (int b = 0; b < nblocks; b++) { s += d.red[b]; q = fmax(q, d.red[kCostBlocks + b]); }
     double ct = s / (double)d.n;
     ct = limit_scaling(fmax(ct, limit_scaling(q)));
     ct = 1.0 / ct;
@@ -1731,7 +1744,8 @@ cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma,
   for (int it = 0; it < scaling_iters; it++) {
     k_ruiz_norms<<<gw, 256, 0, st>>>(d);
     k_ruiz_apply<<<gw, 256, 0, st>>>(d);
-    k_ruiz_cost<<<1, 1024, 0, st>>>(d);
+    k_ruiz_cost_partial<<<kCostBlocks, 256, 0, st>>>(d);
+    k_ruiz_cost<<<1, 32, 0, st>>>(d, kCostBlocks);
     k_ruiz_cost_apply<<<ge, 256, 0, st>>>(d);
   }
   k_scale_finish<<<ew_grid(rows), 256, 0, st>>>(d, scaling_iters > 0 ? 1 : 0);

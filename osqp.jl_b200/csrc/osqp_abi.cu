@@ -457,7 +457,7 @@ c_int pull_state(Engine &e) {
 // scale_data (a2) + set_rho_vec (a3) + preconditioner; `keep_rho_types`: libosqp's update_P/A keeps rho_vec
 c_int rescale_and_refresh(Engine &e, bool reset_rho_types) {
   CU_OK(launch_scale_data(e.d, (int)e.st.scaling, e.st.sigma, e.stream));
-  e.prof.launches += 2 + 4 * (int)e.st.scaling;
+  e.prof.launches += 2 + 5 * (int)e.st.scaling;
   if (reset_rho_types) {
     CU_OK(launch_set_rho_vec(e.d, e.st.rho, 0, e.stream));
     e.prof.launches += 1;
@@ -830,7 +830,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   CU_OK(dalloc(e, &d.m_start, e.geom.grid + 1));
   CU_OK(dalloc(e, &d.n_start, e.geom.grid + 1));
   CU_OK(dalloc(e, &d.bar, 2));
-  CU_OK(dalloc(e, &d.red, (size_t)2 * kRedSlots * e.geom.grid));
+  CU_OK(dalloc(e, &d.red, std::max<size_t>((size_t)2 * kRedSlots * e.geom.grid, 512)));  // >= 2 x 148: k_ruiz_cost_partial
   CU_OK(dalloc(e, &d.dbg, (size_t)16 * e.geom.grid));
   CU_OK(dalloc(e, &d.state, 1));
   CU_OK(dalloc(e, &d.info, 1));
@@ -954,6 +954,10 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   e.prof.spmv_bytes_A = spmv_bytes(nnzA, m, n);
   e.prof.spmv_bytes_At = spmv_bytes(nnzA, n, m);
   e.prof.spmv_bytes_P = spmv_bytes(nnzP, n, n);
+  e.prof.streams = d.blocked;
+  e.prof.groups_A = d.blocked ? d.SA.ngroups : 0;
+  e.prof.groups_At = (d.blocked && m > 0) ? d.ST.ngroups : 0;
+  e.prof.paired = d.blocked ? d.SA.paired : 0;
   publish(e);
   e.info.setup_time = now_s() - t0;
   if (e.st.verbose) print_setup_header(e);

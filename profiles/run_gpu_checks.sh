@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-(OSQP_B200_DEBUG=1 timeout 900 python -m pytest tests/test_engine_parity.py -m gpu -q -x -k "kkt or agree or unconstrained" > gpurun_out/pytest_scale.log 2>&1); grep -E "osqp_b200\] tile|passed|failed|Error|error" gpurun_out/pytest_scale.log | tail -20
+(timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4)
+(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log
+(timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err); cat gpurun_out/bench.json | cut -c1-3000
