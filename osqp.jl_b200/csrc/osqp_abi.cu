@@ -444,6 +444,24 @@ c_int upload_partition(Engine &e, const std::vector<int> &A_rowptr, const std::v
   return 0;
 }
 
+// The cluster-pair layout of the [A; P] stream is also a valid unpaired layout (every block still writes its partial
+// row sums to part[group][row] and the owners add them), so a clustered cooperative launch that the runtime refuses
+// (seen under ncu's launch interception) falls back to the plain cooperative launch for the rest of the workspace.
+template <typename Launch>
+cudaError_t launch_with_pair_fallback(Engine &e, Launch launch) {
+  cudaError_t err = launch();
+  if (err != cudaSuccess && e.geom.cluster > 1) {
+    cudaGetLastError();
+    fprintf(stderr, "WARNING osqp_b200: clustered cooperative launch refused (%s); continuing without cluster pairs\n",
+            cudaGetErrorString(err));
+    e.geom.cluster = 1;
+    e.d.SA.paired = 0;
+    e.prof.paired = 0;
+    err = launch();
+  }
+  return err;
+}
+
 c_int push_state(Engine &e) {
   CU_OK(cudaMemcpyAsync(e.d.state, e.h_state, sizeof(DevState), cudaMemcpyHostToDevice, e.stream));
   return 0;
@@ -989,7 +1007,7 @@ c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
   if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
 
   CU_OK(cudaEventRecord(e.ev0, e.stream));
-  CU_OK(launch_solve(e.d, c, e.geom, e.stream));
+  CU_OK(launch_with_pair_fallback(e, [&]() { return launch_solve(e.d, c, e.geom, e.stream); }));
   CU_OK(cudaEventRecord(e.ev1, e.stream));
   e.prof.launches += 1;
   const int n = e.d.n, m = e.d.m;
@@ -1057,7 +1075,7 @@ c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
     pc.pcg_max_iter = std::max(50, std::min(20 * n, 20000));
     pc.scaling = c.scaling;
     pc.scaled_termination = c.scaled_termination;
-    CU_OK(launch_polish(e.d, pc, c, e.d_pol, e.geom, e.stream));
+    CU_OK(launch_with_pair_fallback(e, [&]() { return launch_polish(e.d, pc, c, e.d_pol, e.geom, e.stream); }));
     CU_OK(cudaEventRecord(e.ev2, e.stream));
     e.prof.launches += 1;
     CU_OK(cudaMemcpyAsync(e.h_pol, e.d_pol, sizeof(PolishOut), cudaMemcpyDeviceToHost, e.stream));
@@ -1364,7 +1382,9 @@ c_int osqp_b200_spmv(OSQPWorkspace *work, c_int which, const c_float *in_host, c
   double *din = (wm == 1) ? e.d.tr : e.d.uu;
   double *dout = (wm == 0) ? e.d.t : e.d.w;
   { c_int rc = upload_vector(e, din, in_host, in_len); if (rc) return rc; }
-  CU_OK(launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream));  // warm-up
+  CU_OK(launch_with_pair_fallback(e, [&]() {  // warm-up
+    return launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream);
+  }));
   CU_OK(cudaEventRecord(e.ev0, e.stream));
   for (c_int r = 0; r < reps; r++) CU_OK(launch_spmv(e.d, (int)which, din, dout, e.st.sigma, e.geom, e.stream));
   CU_OK(cudaEventRecord(e.ev1, e.stream));

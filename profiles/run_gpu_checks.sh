@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-(timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -4)
-(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log
-(timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err); cat gpurun_out/bench.json | cut -c1-3000
+(OSQP_B200_PAIRS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r1h_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1); tail -c 200 gpurun_out/ncu_bench.log
+(OSQP_B200_PAIRS=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"admm_kernel" -s 1 -c 1 -o gpurun_out/r1h_admm python profiles/profile_driver.py --solves 2 --spmv-reps 1 > gpurun_out/ncu_admm.log 2>&1); tail -2 gpurun_out/ncu_admm.log
