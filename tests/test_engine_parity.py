@@ -260,3 +260,39 @@ def test_unconstrained_large_uses_streams(pkg, engine_lib):
     assert r.info.status == "Solved"
     assert np.max(np.abs(P @ r.x + q)) <= 1e-6
     mdl.clean()
+
+
+def test_infeasibility_detected_at_stream_size(pkg, engine_lib, oracle_lib):
+    # test/primal_infeasibility.jl and test/dual_infeasibility.jl at a size that runs on the tile streams
+    prob = random_qp(4000, 8000, 0.01, 51)
+    opts = dict(verbose=False, eps_abs=1e-5, eps_rel=1e-5, eps_prim_inf=1e-5, eps_dual_inf=1e-5, adaptive_rho=False,
+                check_termination=5, max_iter=5000)
+    # primal infeasible: two rows with the same coefficients and disjoint intervals
+    A = prob["A"].tolil()
+    A[1, :] = A[0, :]
+    l, u = prob["l"].copy(), prob["u"].copy()
+    l[0], u[0] = 1.0, 2.0
+    l[1], u[1] = -2.0, -1.0
+    pinf = dict(prob, A=A.tocsc(), l=l, u=u)
+    r = solve_both(pkg, engine_lib, oracle_lib, pinf, opts, oracle_pcg=True)
+    e, o = r["engine"][1], r["oracle"][1]
+    assert e.info.status == o.info.status == "Primal_infeasible", (e.info.status, o.info.status)
+    assert np.all(np.isnan(e.x))
+    # the certificate: dy' A ~ 0 and u' dy+ + l' dy- < 0 (workspace.delta_y, src/interface.jl:195-202)
+    dy = e.prim_inf_cert
+    assert np.max(np.abs(pinf["A"].T @ dy)) <= 1e-3 * np.max(np.abs(dy))
+    assert u @ np.maximum(dy, 0) + l @ np.minimum(dy, 0) < 0
+    # dual infeasible: a free variable without curvature and a cost that pushes it to infinity
+    P = prob["P"].tolil()
+    A2 = prob["A"].tolil()
+    P[7, :] = 0
+    P[:, 7] = 0
+    A2[:, 7] = 0
+    q = prob["q"].copy()
+    q[7] = -1.0
+    dinf = dict(prob, P=P.tocsc(), A=A2.tocsc(), q=q)
+    r = solve_both(pkg, engine_lib, oracle_lib, dinf, opts, oracle_pcg=True)
+    e, o = r["engine"][1], r["oracle"][1]
+    assert e.info.status == o.info.status == "Dual_infeasible", (e.info.status, o.info.status)
+    dx = e.dual_inf_cert  # workspace.delta_x, src/interface.jl:203-209
+    assert abs(dx[7]) == np.max(np.abs(dx)) and q @ dx < 0
