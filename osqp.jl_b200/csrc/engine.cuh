@@ -16,6 +16,8 @@ namespace osqpb200 {
 
 constexpr int kMaxBlocks = 1184;      // 148 SMs x 8
 constexpr int kRedSlots = 32;         // scalars reduced per grid barrier
+constexpr int kFxSlots = 8;           // fixed-point accumulators per bank (the last one is the overflow flag)
+constexpr int kBarBytes = 16 + 3 * kFxSlots * 8;  // DevPtrs::bar: arrival counter, then 3 banks of accumulators
 constexpr int kLogRows = 64;          // verbose table rows buffered per solve
 constexpr int kPhases = 16;           // phase classes timed by block 0 (include/osqp_b200.h OSQPB200Profile.phase_us)
 
@@ -132,7 +134,7 @@ struct DevPtrs {
   // work partition: block b owns rows [m_start[b], m_start[b+1]) of A and [n_start[b], n_start[b+1]) of P/A'
   int *m_start = nullptr, *n_start = nullptr;
   // grid barrier + reductions
-  unsigned *bar = nullptr;  // [0] arrival count, [1] generation
+  unsigned *bar = nullptr;  // kBarBytes: [0] arrival count, from byte 16: fixed-point accumulator banks
   double *red = nullptr;    // [2][kRedSlots][grid]
   DevState *state = nullptr;
   DevInfo *info = nullptr;

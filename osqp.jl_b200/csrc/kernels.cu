@@ -327,8 +327,9 @@ __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDe
 struct Grid {
   unsigned *count;
   unsigned nblocks, target;
-  int bank;
+  int bank, fbank;
   double *red;
+  unsigned long long *facc;  // [3][kFxSlots] fixed-point accumulators of reduce_and_barrier_fx (zero at launch)
 };
 
 __device__ __forceinline__ void grid_init(Grid &g, const DevPtrs &d) {
@@ -336,7 +337,9 @@ __device__ __forceinline__ void grid_init(Grid &g, const DevPtrs &d) {
   g.nblocks = gridDim.x;
   g.target = 0u;
   g.bank = 0;
+  g.fbank = 0;
   g.red = d.red;
+  g.facc = reinterpret_cast<unsigned long long *>(d.bar + 4);
 }
 
 __device__ __forceinline__ void grid_barrier(Grid &g) {
@@ -357,6 +360,7 @@ __device__ __forceinline__ void grid_barrier(Grid &g) {
 struct RedSmem {
   double part[kWarps][kRedSlots];  // the cooperative kernels run kThreads = 32 * kWarps threads per block
   double res[kRedSlots];
+  unsigned long long fx[kFxSlots];
 };
 
 template <int NV>
@@ -375,16 +379,18 @@ __device__ __forceinline__ void reduce_and_barrier(Grid &g, RedSmem &sm, double 
     if (lane == 0) sm.part[warp][k] = a;
   }
   __syncthreads();
-  if (threadIdx.x < NV) {
-    const int k = threadIdx.x;
-    double a = sm.part[0][k];
-    if (maxmask & (1u << k)) {
-      for (int w = 1; w < nwarps; w++) a = fmax(a, sm.part[w][k]);
-    } else {
-      for (int w = 1; w < nwarps; w++) a += sm.part[w][k];
+  for (int k = warp; k < NV; k += nwarps) {  // one warp per slot: fixed shuffle tree over the warps' partials
+    const bool ismax = maxmask & (1u << k);
+    double a = lane < nwarps ? sm.part[lane][k] : (ismax ? -INFINITY : 0.0);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, a, o);
+      a = ismax ? fmax(a, x) : a + x;
     }
-    if (g.nblocks > 1) g.red[((size_t)g.bank * kRedSlots + k) * g.nblocks + blockIdx.x] = a;
-    else sm.res[k] = a;
+    if (lane == 0) {
+      if (g.nblocks > 1) g.red[((size_t)g.bank * kRedSlots + k) * g.nblocks + blockIdx.x] = a;
+      else sm.res[k] = a;
+    }
   }
   grid_barrier(g);
   if (g.nblocks > 1) {
@@ -409,6 +415,96 @@ __device__ __forceinline__ void reduce_and_barrier(Grid &g, RedSmem &sm, double 
 #pragma unroll
   for (int k = 0; k < NV; k++) v[k] = sm.res[k];
   __syncthreads();  // sm.res may be rewritten by the next reduction
+}
+
+// Same contract, for the reductions inside the PCG iteration: the cross-block stage is done by the L2 atomic units
+// instead of 148 loads per block after the barrier.  Sums are accumulated as 64-bit fixed point (integer addition is
+// associative: bit-identical from run to run, like the fixed-order tree), scaled so that `ref` -- a positive value
+// every thread of the grid holds identically and that is within a few binary orders of the result -- sits at 2^50;
+// maxima of non-negative values use atomicMax on the bit pattern.  A block whose partial does not fit (|.| >= 2^55
+// after scaling, or not finite) raises a flag and every block then finishes through the plain two-level path on the
+// fp64 partials that are always written as well.  Three accumulator banks: call k uses bank k % 3 and block 0
+// clears bank (k + 2) % 3 after the barrier of call k (its last readers finished before arriving at that barrier,
+// its next writers start after the barrier of call k + 1).
+template <int NV>
+__device__ __forceinline__ void reduce_and_barrier_fx(Grid &g, RedSmem &sm, double (&v)[NV], unsigned maxmask,
+                                                      double ref) {
+  static_assert(NV < kFxSlots, "one slot is the overflow flag");
+  if (!(g.nblocks > 1 && isfinite(ref) && ref > 0.0)) {  // uniform over the grid
+    reduce_and_barrier<NV>(g, sm, v, maxmask);
+    return;
+  }
+  const double scale = scalbn(1.0, 50 - ilogb(ref));
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NV; k++) {
+    double a = v[k];
+    if (maxmask & (1u << k)) {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a = fmax(a, __shfl_xor_sync(0xffffffffu, a, o));
+    } else {
+#pragma unroll
+      for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    }
+    if (lane == 0) sm.part[warp][k] = a;
+  }
+  __syncthreads();
+  unsigned long long *acc = g.facc + g.fbank * kFxSlots;
+  if (warp < NV) {  // one warp per slot: fixed shuffle tree over the warps' partials, lane 0 feeds the L2 atomic
+    const int k = warp;
+    const bool ismax = maxmask & (1u << k);
+    double a = lane < nwarps ? sm.part[lane][k] : (ismax ? -INFINITY : 0.0);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const double x = __shfl_xor_sync(0xffffffffu, a, o);
+      a = ismax ? fmax(a, x) : a + x;
+    }
+    if (lane == 0) {
+      g.red[((size_t)g.bank * kRedSlots + k) * g.nblocks + blockIdx.x] = a;  // for the fallback
+      if (ismax) {
+        if (a >= 0.0 && isfinite(a)) atomicMax(acc + k, (unsigned long long)__double_as_longlong(a));
+        else atomicMax(acc + kFxSlots - 1, 1ull);
+      } else {
+        const double sc = a * scale;
+        if (fabs(sc) < 36028797018963968.0) atomicAdd(acc + k, (unsigned long long)__double2ll_rn(sc));
+        else atomicMax(acc + kFxSlots - 1, 1ull);
+      }
+    }
+  }
+  grid_barrier(g);
+  if (threadIdx.x < kFxSlots) {
+    sm.fx[threadIdx.x] = __ldcg(acc + threadIdx.x);
+    if (blockIdx.x == 0) g.facc[((g.fbank + 2) % 3) * kFxSlots + threadIdx.x] = 0ull;
+  }
+  __syncthreads();
+  if (sm.fx[kFxSlots - 1] != 0ull) {  // uniform: somebody's partial did not fit
+    for (int k = warp; k < NV; k += nwarps) {
+      const double *src = g.red + ((size_t)g.bank * kRedSlots + k) * g.nblocks;
+      const bool ismax = maxmask & (1u << k);
+      double a = ismax ? -INFINITY : 0.0;
+      for (unsigned i = lane; i < g.nblocks; i += 32) {
+        double x = __ldcg(src + i);
+        a = ismax ? fmax(a, x) : a + x;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        double x = __shfl_xor_sync(0xffffffffu, a, o);
+        a = ismax ? fmax(a, x) : a + x;
+      }
+      if (lane == 0) sm.res[k] = a;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; k++) v[k] = sm.res[k];
+  } else {
+    const double inv = 1.0 / scale;  // a power of two: exact
+#pragma unroll
+    for (int k = 0; k < NV; k++)
+      v[k] = (maxmask & (1u << k)) ? __longlong_as_double((long long)sm.fx[k]) : (double)(long long)sm.fx[k] * inv;
+  }
+  g.bank ^= 1;
+  g.fbank = (g.fbank + 1) % 3;
+  __syncthreads();  // sm.fx / sm.res may be rewritten by the next reduction
 }
 
 // ------------------------------------------------------------------ row-parallel SpMV building block
@@ -633,7 +729,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     }
     pc.tick(2);
     if (m > 0) {
-      reduce_and_barrier<1>(g, sm, red1, 0u);
+      reduce_and_barrier_fx<1>(g, sm, red1, 0u, gamma);  // delta / gamma is a Rayleigh quotient of M^-1 K
       pc.tick(3);
       // ---- phase B
       stream_phase(S, d.ST, v.tr);
@@ -686,7 +782,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       }
     }
     pc.tick(6);
-    reduce_and_barrier<2>(g, sm, red2, 0x2u);
+    reduce_and_barrier_fx<2>(g, sm, red2, 0x2u, gamma);
     pc.tick(7);
     gamma_old = gamma;
     gamma = red2[0];
@@ -1442,7 +1538,7 @@ __global__ void __launch_bounds__(kThreads, 1) membench_kernel(const char *buf, 
 }
 
 // ------------------------------------------------------------------ barrier micro-benchmark (profiles/membench.py)
-// mode 0: `iters` bare grid barriers | 1: reduce_and_barrier<2> | 2: barrier after 1000 scattered 8 B stores per block
+// mode 0: `iters` bare grid barriers | 1: reduce_and_barrier<2> | 2: barrier after scattered 8 B stores | 3: reduce_and_barrier_fx<2>
 __global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const DevPtrs d, int iters, int mode, double *sink,
                                                                     unsigned long long *ns_out) {
   __shared__ RedSmem sm;
@@ -1455,6 +1551,10 @@ __global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const DevPtr
     if (mode == 1) {
       double v[2] = {1.0 + acc, (double)threadIdx.x};
       reduce_and_barrier<2>(g, sm, v, 0x2u);
+      acc = v[0] * 1e-9;
+    } else if (mode == 3) {
+      double v[2] = {1.0 + acc, (double)threadIdx.x};
+      reduce_and_barrier_fx<2>(g, sm, v, 0x2u, 1.0e5);
       acc = v[0] * 1e-9;
     } else {
       if (mode == 2 && (threadIdx.x & 31) < 2) sink[64 + ((size_t)blockIdx.x * 1024 + threadIdx.x * 17 + it) % 100000] = acc;
@@ -1711,7 +1811,7 @@ inline int ew_grid(long long work) {
 
 template <typename... Args>
 cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cudaStream_t st, Args... args) {
-  cudaError_t e = cudaMemsetAsync(bar, 0, 2 * sizeof(unsigned), st);  // grid barrier arrival counter
+  cudaError_t e = cudaMemsetAsync(bar, 0, kBarBytes, st);  // grid barrier arrival counter + fixed-point accumulators
   if (e != cudaSuccess) return e;
   void *params[] = {(void *)&args...};
   if (g.cluster <= 1)

@@ -847,7 +847,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   CU_OK(dalloc(e, &d.ctype, m));
   CU_OK(dalloc(e, &d.m_start, e.geom.grid + 1));
   CU_OK(dalloc(e, &d.n_start, e.geom.grid + 1));
-  CU_OK(dalloc(e, &d.bar, 2));
+  CU_OK(dalloc(e, &d.bar, kBarBytes / sizeof(unsigned)));
   CU_OK(dalloc(e, &d.red, std::max<size_t>((size_t)2 * kRedSlots * e.geom.grid, 512)));  // >= 2 x 148: k_ruiz_cost_partial
   CU_OK(dalloc(e, &d.dbg, (size_t)16 * e.geom.grid));
   CU_OK(dalloc(e, &d.state, 1));

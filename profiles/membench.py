@@ -19,7 +19,8 @@ prob = bench.make_problem(bench.N_VARS, bench.N_CONS, bench.DENSITY, bench.SEED)
 mdl = pkg.Model(lib=graft.LIB); mdl.setup(**prob, **bench.SETTINGS)
 eng.osqp_b200_barrier_bench.restype = C.c_double
 eng.osqp_b200_barrier_bench.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
-for mode, name in ((0, "bare grid barrier"), (1, "reduce_and_barrier<2>"), (2, "barrier after scattered stores")):
+for mode, name in ((0, "bare grid barrier"), (1, "reduce_and_barrier<2>"), (2, "barrier after scattered stores"),
+                   (3, "reduce_and_barrier_fx<2>")):
     print(f"{name:32s} {eng.osqp_b200_barrier_bench(mdl.workspace, 2000, mode):8.0f} ns")
 eng.osqp_b200_cluster_probe.restype = C.c_longlong
 eng.osqp_b200_cluster_probe.argtypes = [C.c_void_p, C.c_longlong]

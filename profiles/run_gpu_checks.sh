@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_engine_parity.py -m gpu -q -x -k "infeasib" > gpurun_out/pytest_inf.log 2>&1); tail -15 gpurun_out/pytest_inf.log
+(timeout 300 python profiles/membench.py 2>&1 | tail -6)
+(timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -4)
+(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log
