@@ -48,6 +48,7 @@ struct CsrDev {
 //     element-wise phase that follows the next grid barrier (fixed order -> run-to-run deterministic).
 constexpr int kWarps = 16;          // warps per thread block of the cooperative kernels (kThreads / 32)
 constexpr int kSliceMax = 27648;    // doubles per staged slice (216 KB); local columns are 15-bit
+constexpr int kSplitQuads = 64;     // smallest piece a long row is cut into (build_tile_stream: stream rows)
 
 struct TileStreamDev {
   int rows = 0, cols = 0;        // stacked rows, length of the gathered vector
@@ -67,7 +68,10 @@ struct TileStreamDev {
   int *w_row0 = nullptr;         // [grid * kWarps] first stacked row of warp i
   int *w_q0 = nullptr;           // [grid * kWarps + 1] first quad of warp i's stream (a multiple of 32 = one chunk)
   int *w_qn = nullptr;           // [grid * kWarps] quads in warp i's stream
-  double *part = nullptr;        // [ngroups][rows] partial row sums of the last phase
+  int split = 0;                 // 1: some rows are cut into several stream rows (engine.cuh kSplitQuads)
+  int srows = 0;                 // stream rows per group (stride of `part`); == rows when nothing is split
+  int *sr_ptr = nullptr;         // [ngroups][rows + 1] first stream row of each row (identity when split == 0)
+  double *part = nullptr;        // [ngroups][srows] partial sums of the stream rows of the last phase
 };
 
 // Persistent solver state that survives between launches (device memory).

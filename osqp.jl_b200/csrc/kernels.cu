@@ -209,7 +209,7 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     if (warp == 0) mbar_wait(S.mbar, parity);
     return;
   }
-  double *__restrict__ out = T.part + (size_t)grp * T.rows + __ldg(T.w_row0 + wid);
+  double *__restrict__ out = T.part + (size_t)grp * T.srows + __ldg(T.w_row0 + wid);
   const unsigned out_s = kPair ? S.ys + 8u * (unsigned)(__ldg(T.w_row0 + wid) - __ldg(T.blk_row0 + b)) : 0u;
   const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * q0 + 16 * lane;
   const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
@@ -649,8 +649,16 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
 
 // Owner-side sum of the per-group partial row sums of a tile-stream phase (fixed order).
 __device__ __forceinline__ double part_sum(const TileStreamDev &T, int row) {
-  double a = T.part[row];
-  for (int g = 1; g < T.ngroups; g++) a += T.part[(size_t)g * T.rows + row];
+  if (!T.split) {
+    double a = T.part[row];
+    for (int g = 1; g < T.ngroups; g++) a += T.part[(size_t)g * T.srows + row];
+    return a;
+  }
+  double a = 0.0;  // rows cut into pieces: add the pieces of every group in order
+  for (int g = 0; g < T.ngroups; g++) {
+    const int *sp = T.sr_ptr + (size_t)g * (T.rows + 1) + row;
+    for (int sr = __ldg(sp); sr < __ldg(sp + 1); sr++) a += T.part[(size_t)g * T.srows + sr];
+  }
   return a;
 }
 

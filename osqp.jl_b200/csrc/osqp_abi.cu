@@ -242,8 +242,8 @@ struct TileStreamHost {
   int rows = 0, cols = 0, ngroups = 0;
   long long nelem = 0, nnz = 0;
   std::vector<unsigned short> cf;
-  std::vector<int> from_csr, blk_group, blk_row0, blk_row1, grp_col0, w_row0, w_q0, w_qn;
-  int max_slice = 0, max_block_rows = 0, paired = 0;
+  std::vector<int> from_csr, blk_group, blk_row0, blk_row1, grp_col0, w_row0, w_q0, w_qn, sr_ptr;
+  int max_slice = 0, max_block_rows = 0, paired = 0, split = 0, srows = 0;
 };
 
 // false: the stream does not pay off for this matrix (too much padding) -> CSR path
@@ -274,13 +274,40 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   }
   // quads of a row inside a group (a row without entries there still costs one zero quad)
   auto quads_of = [](int c) { return std::max(1, (c + 3) >> 2); };
+  // Stream rows.  A row with more than `split_quads` quads in a group is cut into pieces of that many quads, each
+  // piece a row of its own for the stream (own row-end flag, own partial sum): a warp owns whole stream rows, so
+  // without the cut one dense row would serialise on a single warp.  sr_ptr[g][r] = first stream row of row r.
+  // Pieces are only as small as balance needs: a quarter of the mean load of a warp, at least kSplitQuads.
+  T.sr_ptr.assign((size_t)ngroups * (rows + 1), 0);
+  T.split = 0;
+  T.srows = rows;
+  long long all_quads = 0;
+  for (size_t i = 0; i < cnt.size(); i++) all_quads += quads_of(cnt[i]);
+  const int split_quads = (int)std::max<long long>(kSplitQuads, all_quads / ((long long)grid * kWarps) / 4);
+  for (int g = 0; g < ngroups; g++) {
+    int *sp = T.sr_ptr.data() + (size_t)g * (rows + 1);
+    for (int r = 0; r < rows; r++) sp[r + 1] = sp[r] + (quads_of(cnt[(size_t)r * ngroups + g]) + split_quads - 1) / split_quads;
+    if (sp[rows] != rows) T.split = 1;
+    T.srows = std::max(T.srows, sp[rows]);
+  }
+  if (T.split) paired = false;  // the DSMEM combine of a pair works row by row
+  // weight prefix per group over its stream rows
+  std::vector<std::vector<long long>> wpre(ngroups);
   std::vector<long long> gw(ngroups, 0);
-  std::vector<long long> wpre((size_t)ngroups * (rows + 1), 0);
   long long stored = 0;
   for (int g = 0; g < ngroups; g++) {
-    long long *wp = wpre.data() + (size_t)g * (rows + 1);
-    for (int r = 0; r < rows; r++) wp[r + 1] = wp[r] + quads_of(cnt[(size_t)r * ngroups + g]);
-    gw[g] = wp[rows];
+    const int *sp = T.sr_ptr.data() + (size_t)g * (rows + 1);
+    std::vector<long long> &wp = wpre[g];
+    wp.assign((size_t)sp[rows] + 1, 0);
+    for (int r = 0; r < rows; r++) {
+      int q = quads_of(cnt[(size_t)r * ngroups + g]);
+      for (int s = sp[r]; s < sp[r + 1]; s++) {
+        const int piece = std::min(q, split_quads);
+        wp[s + 1] = wp[s] + piece;
+        q -= piece;
+      }
+    }
+    gw[g] = wp[sp[rows]];
     stored += 4 * gw[g];
   }
   if (nnz > 0 && (double)stored > 1.35 * (double)nnz + 4096.0) return false;  // padding would dominate
@@ -310,8 +337,8 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   T.w_row0.assign((size_t)grid * kWarps, 0);
   T.w_q0.assign((size_t)grid * kWarps + 1, 0);
   std::vector<int> w_row1((size_t)grid * kWarps, 0);
-  // contiguous split of rows [ra, rb) into `parts` ranges balanced on a weight prefix (every range that still has
-  // rows gets at least one)
+  // contiguous split of (stream) rows [ra, rb) into `parts` ranges balanced on a weight prefix (every range that
+  // still has rows gets at least one)
   auto split = [&](const long long *wp, int ra, int rb, int parts, std::vector<int> &cut, int max_rows = 1 << 30) {
     cut.assign(parts + 1, rb);
     int r = ra;
@@ -331,9 +358,9 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   std::vector<int> cut;
   if (paired) {
     // cluster pairs: blocks 2p (group 0) and 2p+1 (group 1) stream the SAME row range p; ranges are balanced on the
-    // combined weight so both halves of a pair finish together
+    // combined weight so both halves of a pair finish together  (no split rows here: stream rows == rows)
     std::vector<long long> wsum(rows + 1, 0);
-    for (int r = 0; r <= rows; r++) wsum[r] = wpre[r] + wpre[(size_t)(rows + 1) + r];
+    for (int r = 0; r <= rows; r++) wsum[r] = wpre[0][r] + wpre[1][r];
     if ((long long)(grid / 2) * max_pair_rows < rows) return false;
     split(wsum.data(), 0, rows, grid / 2, cut, max_pair_rows);
     for (int b = 0; b < grid; b++) {
@@ -344,7 +371,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   } else {
     int b0 = 0;
     for (int g = 0; g < ngroups; g++) {
-      split(wpre.data() + (size_t)g * (rows + 1), 0, rows, nblk[g], cut);
+      split(wpre[g].data(), 0, (int)wpre[g].size() - 1, nblk[g], cut);
       for (int bb = 0; bb < nblk[g]; bb++) {
         T.blk_group[b0 + bb] = g;
         T.blk_row0[b0 + bb] = cut[bb];
@@ -357,27 +384,27 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   for (int b = 0; b < grid; b++) {
     const int g = T.blk_group[b];
     T.max_block_rows = std::max(T.max_block_rows, T.blk_row1[b] - T.blk_row0[b]);
-    split(wpre.data() + (size_t)g * (rows + 1), T.blk_row0[b], T.blk_row1[b], kWarps, cut);
+    split(wpre[g].data(), T.blk_row0[b], T.blk_row1[b], kWarps, cut);
     for (int w = 0; w < kWarps; w++) {
       T.w_row0[(size_t)b * kWarps + w] = cut[w];
       w_row1[(size_t)b * kWarps + w] = cut[w + 1];
     }
   }
   if (getenv("OSQP_B200_DEBUG"))
-    fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d max_block_rows=%d\n", rows, cols, ngroups, T.paired,
-            T.max_block_rows);
-  // positions: warp by warp, row by row; every row segment is a whole number of quads and every warp's stream
-  // starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
-  std::vector<int> seg_start((size_t)rows * ngroups, 0);
+    fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d split=%d stream rows=%d max_block_rows=%d\n", rows, cols,
+            ngroups, T.paired, T.split, T.srows, T.max_block_rows);
+  // positions: warp by warp, stream row by stream row; every stream row is a whole number of quads and every warp's
+  // stream starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
+  std::vector<std::vector<int>> sr_start(ngroups);
+  for (int g = 0; g < ngroups; g++) sr_start[g].assign(wpre[g].size(), 0);
   T.w_qn.assign((size_t)grid * kWarps, 0);
   long long pos = 0;
   for (int wid = 0; wid < grid * kWarps; wid++) {
     const int g = T.blk_group[wid / kWarps];
     T.w_q0[wid] = (int)(pos / 4);
-    for (int r = T.w_row0[wid]; r < w_row1[wid]; r++) {
-      const size_t si = (size_t)r * ngroups + g;
-      seg_start[si] = (int)pos;
-      pos += 4 * quads_of(cnt[si]);
+    for (int sr = T.w_row0[wid]; sr < w_row1[wid]; sr++) {
+      sr_start[g][sr] = (int)pos;
+      pos += 4 * (wpre[g][sr + 1] - wpre[g][sr]);
     }
     T.w_qn[wid] = (int)(pos / 4) - T.w_q0[wid];
     pos = (pos + 127) & ~127LL;
@@ -387,7 +414,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   T.nelem = pos;
   T.cf.assign((size_t)pos + 8, 0);
   T.from_csr.resize(nnz);
-  std::vector<int> cursor(seg_start);
+  std::vector<int> cursor((size_t)rows * ngroups, 0);  // entries of (row, group) placed so far
   {
     int r0 = 0;
     long long k0 = 0;
@@ -395,7 +422,9 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       for (int r = 0; r < M.rows; r++)
         for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) {
           const int c = (*M.col)[k], g = c / Wg;
-          const int p = cursor[(size_t)(r0 + r) * ngroups + g]++;
+          const int e = cursor[(size_t)(r0 + r) * ngroups + g]++;
+          const int piece = (e >> 2) / split_quads;
+          const int p = sr_start[g][T.sr_ptr[(size_t)g * (rows + 1) + r0 + r] + piece] + (e - 4 * split_quads * piece);
           T.cf[p] = (unsigned short)(c - g * Wg);
           T.from_csr[k0 + k] = stream_val_pos(p);
         }
@@ -403,23 +432,26 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       k0 += (*M.rowptr)[M.rows];
     }
   }
-  for (size_t si = 0; si < (size_t)rows * ngroups; si++) T.cf[seg_start[si] + 4 * quads_of(cnt[si]) - 1] |= 0x8000u;
+  for (int g = 0; g < ngroups; g++)
+    for (size_t sr = 0; sr + 1 < wpre[g].size(); sr++)
+      T.cf[sr_start[g][sr] + 4 * (wpre[g][sr + 1] - wpre[g][sr]) - 1] |= 0x8000u;
   return true;
 }
 
 c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
   t.variant = env_int("OSQP_B200_STREAM_VARIANT", 0);
   t.rows = h.rows; t.cols = h.cols; t.ngroups = h.ngroups; t.nelem = h.nelem;
+  t.split = h.split; t.srows = h.srows;
   t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 8))) & ~3;
   CU_OK(dalloc(e, &t.val, (size_t)h.nelem + 8));
   CU_OK(dalloc(e, &t.cf, (size_t)h.nelem + 8));
   CU_OK(dalloc(e, &t.from_csr, (size_t)h.nnz));
-  CU_OK(dalloc(e, &t.part, (size_t)h.ngroups * h.rows + 8));
+  CU_OK(dalloc(e, &t.part, (size_t)h.ngroups * h.srows + 8));
 #define UP(dst, vec)                                                                                         \
   CU_OK(dalloc(e, &dst, (vec).size()));                                                                      \
   CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
   UP(t.blk_group, h.blk_group); UP(t.grp_col0, h.grp_col0); UP(t.w_row0, h.w_row0); UP(t.w_q0, h.w_q0);
-  UP(t.w_qn, h.w_qn); UP(t.blk_row0, h.blk_row0); UP(t.blk_row1, h.blk_row1);
+  UP(t.w_qn, h.w_qn); UP(t.blk_row0, h.blk_row0); UP(t.blk_row1, h.blk_row1); UP(t.sr_ptr, h.sr_ptr);
   t.paired = h.paired;
 #undef UP
   CU_OK(cudaMemcpyAsync(t.cf, h.cf.data(), (size_t)h.nelem * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
@@ -433,9 +465,15 @@ c_int upload_partition(Engine &e, const std::vector<int> &A_rowptr, const std::v
                        const std::vector<int> &P_rowptr, std::vector<int> &ms, std::vector<int> &ns) {
   const int n = e.d.n, m = e.d.m, grid = e.geom.grid;
   std::vector<long long> wm(m + 1, 0), wn(n + 1, 0);
-  for (int i = 0; i < m; i++) wm[i + 1] = wm[i] + (A_rowptr[i + 1] - A_rowptr[i]) + 4;
+  // Ownership serves two kinds of work: the element-wise owner phases of every PCG iteration (cost per ROW: one L2
+  // round trip per 512 rows of a block) and the CSR products of update_info / the residual refresh (cost per
+  // NON-ZERO, once per 25 ADMM iterations).  A row therefore weighs its non-zeros plus a constant that dominates for
+  // short rows: a block that owns only one-entry rows (identity blocks of a Lasso / MPC matrix) must not own 100x
+  // more rows than the others.
+  const long long kRowCost = 256;
+  for (int i = 0; i < m; i++) wm[i + 1] = wm[i] + (A_rowptr[i + 1] - A_rowptr[i]) + kRowCost;
   for (int j = 0; j < n; j++)
-    wn[j + 1] = wn[j] + (P_rowptr[j + 1] - P_rowptr[j]) + (m > 0 ? At_rowptr[j + 1] - At_rowptr[j] : 0) + 4;
+    wn[j + 1] = wn[j] + (P_rowptr[j + 1] - P_rowptr[j]) + (m > 0 ? At_rowptr[j + 1] - At_rowptr[j] : 0) + kRowCost;
   balanced_split(wm, m, grid, ms);
   balanced_split(wn, n, grid, ns);
   CU_OK(cudaMemcpyAsync(e.d.m_start, ms.data(), (grid + 1) * sizeof(int), cudaMemcpyHostToDevice, e.stream));
@@ -587,8 +625,8 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
   }
   std::vector<double> sv((size_t)T.nelem + 8, 0.0);
   for (long long k = 0; k < T.nnz; k++) sv[T.from_csr[k]] = val[k];
-  std::vector<double> part((size_t)T.ngroups * rows, 0.0);
-  std::vector<char> written((size_t)T.ngroups * rows, 0);
+  std::vector<double> part((size_t)T.ngroups * T.srows, 0.0);
+  std::vector<char> written((size_t)T.ngroups * T.srows, 0);
   for (int wid = 0; wid < (int)grid * kWarps; wid++) {
     const int grp = T.blk_group[wid / kWarps];
     const int q0 = T.w_q0[wid], L = T.w_qn[wid];
@@ -597,8 +635,8 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
     if (T.w_row0[wid] < T.blk_row0[wid / kWarps] || T.w_row0[wid] > T.blk_row1[wid / kWarps]) return 11;
     const double *xs = x + T.grp_col0[grp];
     const int slice = T.grp_col0[grp + 1] - T.grp_col0[grp];
-    double *out = part.data() + (size_t)grp * rows + T.w_row0[wid];
-    char *wr = written.data() + (size_t)grp * rows + T.w_row0[wid];
+    double *out = part.data() + (size_t)grp * T.srows + T.w_row0[wid];
+    char *wr = written.data() + (size_t)grp * T.srows + T.w_row0[wid];
     int rdone = 0;
     double carry = 0.0;
     for (int cc = 0; cc < L; cc += 32) {
@@ -621,7 +659,7 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
         }
         run += acc;
         if (flag) {
-          if (T.w_row0[wid] + rdone + nflag >= rows) return 6;
+          if (T.w_row0[wid] + rdone + nflag >= T.srows) return 6;
           out[rdone + nflag] = run;
           wr[rdone + nflag]++;
           nflag++;
@@ -633,10 +671,14 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
     }
     if (carry != 0.0) return 8;  // the last quad of a warp's stream must close its row
   }
-  for (size_t i = 0; i < written.size(); i++) if (written[i] != 1) return 9;
-  for (c_int r = 0; r < rows; r++) {
-    double a = part[r];
-    for (int g = 1; g < T.ngroups; g++) a += part[(size_t)g * rows + r];
+  for (int g = 0; g < T.ngroups; g++)
+    for (int sr = 0; sr < T.sr_ptr[(size_t)g * (rows + 1) + rows]; sr++)
+      if (written[(size_t)g * T.srows + sr] != 1) return 9;
+  for (c_int r = 0; r < rows; r++) {  // part_sum of kernels.cu
+    double a = 0.0;
+    for (int g = 0; g < T.ngroups; g++)
+      for (int sr = T.sr_ptr[(size_t)g * (rows + 1) + r]; sr < T.sr_ptr[(size_t)g * (rows + 1) + r + 1]; sr++)
+        a += part[(size_t)g * T.srows + sr];
     y_out[r] = a;
   }
   return 0;

@@ -10,6 +10,7 @@ import __graft_entry__ as graft, problems
 ap = argparse.ArgumentParser()
 ap.add_argument("--lasso", default="10000,50000,0.15")
 ap.add_argument("--portfolio", default="20000,200")
+ap.add_argument("--lambdas", type=int, default=11)
 args = ap.parse_args()
 pkg = graft.load_package(); eng = pkg.load_library(graft.LIB)
 
@@ -36,7 +37,8 @@ t0 = time.perf_counter()
 mdl.setup(**dict(prob, q=q_of(2 * lam_max)), verbose=False, eps_abs=1e-4, eps_rel=1e-4, adaptive_rho_interval=25, max_iter=4000)
 print(f"  setup {time.perf_counter() - t0:.2f}s")
 tot_it, tot_ms = 0, 0.0
-for lam in np.logspace(0, -2, 11) * 2 * lam_max:
+PH = ["stream[A;P]", "barrier", "combine", "reduce+bar", "stream A'", "barrier", "vectors", "reduce+bar"]
+for lam in (np.logspace(0, -2, 11) * 2 * lam_max)[:args.lambdas]:
     mdl.update(q=q_of(lam))
     r = mdl.solve()
     p = prof(mdl)
@@ -44,6 +46,7 @@ for lam in np.logspace(0, -2, 11) * 2 * lam_max:
     pri, dua = kkt(dict(prob, q=q_of(lam)), r)
     print(f"  lambda={lam:9.3f} {r.info.status} iter={r.info.iter} kernel={p.kernel_ms:.1f} ms pcg/admm={p.pcg_iters / max(1, p.admm_iters):.1f} "
           f"nnz(x)={int(np.sum(np.abs(r.x[:int(nf)]) > 1e-4))} pri={pri:.2e} dua={dua:.2e}")
+print("  per PCG it (us): " + "  ".join(f"{PH[k]} {p.phase_us[k] / max(1, p.pcg_iters):.1f}" for k in range(8)))
 print(f"  lasso sweep: {tot_it} ADMM its in {tot_ms:.1f} ms -> {tot_it / tot_ms * 1e3:.0f} it/s; streams={prof(mdl).streams} groups={prof(mdl).groups_A}/{prof(mdl).groups_At} paired={prof(mdl).paired}")
 mdl.clean()
 

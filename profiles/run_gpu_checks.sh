@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-(timeout 300 python profiles/membench.py 2>&1 | tail -6)
-(timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -4)
-(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log
+(timeout 900 python profiles/configs_full.py --lambdas 3 > gpurun_out/configs_full.log 2>&1); tail -9 gpurun_out/configs_full.log
+(timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep "^solve" | tail -1)

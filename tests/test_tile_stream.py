@@ -90,3 +90,22 @@ def test_stream_declines_hopeless_padding(pkg, engine_lib):
     M = sp.eye(20000, format="csr")
     rc, _, _ = _run(lib, M, np.ones(20000), 148, 2)
     assert rc == 2  # 8 stored entries per one-entry row: the builder must refuse
+
+
+def test_dense_rows_are_split_into_pieces(pkg, engine_lib):
+    # portfolio-like: a few rows with thousands of entries next to many short rows (BASELINE config 4: F' rows)
+    lib = pkg.load_library(engine_lib)
+    rng = np.random.default_rng(11)
+    rows, cols = 3000, 20000
+    M = sp.random(rows, cols, density=0.0005, random_state=rng, data_rvs=rng.standard_normal, format="lil")
+    for r in (0, 17, 1500, 2999):
+        M[r, :] = rng.standard_normal(cols) * (rng.random(cols) < 0.5)
+    M = M.tocsr()
+    x = rng.standard_normal(cols)
+    for ngroups in (1, 2):
+        rc, y, pad = _run(lib, M, x, 148, ngroups)
+        assert rc == 0
+        scale = np.abs(M) @ np.abs(x) + 1e-300
+        assert np.max(np.abs(y - M @ x) / scale) < 1e-13
+    rc, _, _ = _run(lib, M, x, 148, 2, paired=1)
+    assert rc == 2  # split rows and cluster pairs do not combine: the builder falls back to the unpaired layout
