@@ -132,7 +132,25 @@ def run_cpu(pkg, prob, steps, warmup, max_iter):
                        f"oracle PCG backend, {threads} OpenMP threads")
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract goes to the process's original stdout; everything else that anybody prints
+    (NCCL's version banner, verbose solvers, warnings of C libraries) was re-routed to stderr in main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -176,7 +194,7 @@ def main():
             "note": "libosqp 0.6.2 (OSQP_jll) is an un-vendored binary: the CPU arm is the oracle port in its "
                     "reduced-KKT PCG mode; the direct LDL' mode does not fit this pattern in memory",
         }
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ B200 arm
@@ -364,7 +382,7 @@ def main():
             "solve": {"status": status, "admm_iters_per_solve": iters / args.steps, "setup_s": setup_s,
                       "grid": int(p1.grid), "block": int(p1.block), "lanes": [int(p1.lanes_A), int(p1.lanes_N)]},
         }
-        print(json.dumps(line))
+        emit(line)
     mdl.clean()
     if world > 1:
         dist.destroy_process_group()
