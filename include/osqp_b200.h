@@ -114,6 +114,11 @@ c_float osqp_b200_barrier_bench(OSQPWorkspace *work, c_int iters, c_int mode);
 /* Co-resident thread-block clusters of size `csize` for the workspace's persistent kernel (occupancy query). */
 c_int osqp_b200_cluster_probe(OSQPWorkspace *work, c_int csize);
 
+/* Self-test of the grid-wide reductions: every thread of the persistent grid contributes (global index + 1);
+ * out[6] = {sum, max} by the fp64 tree, by the fixed-point atomics scaled with `ref`, and by a second fixed-point
+ * call (0.5 * index as the summand).  A tiny `ref` forces the overflow fallback. */
+c_int osqp_b200_reduce_selftest(OSQPWorkspace *work, c_float ref, c_float *out);
+
 c_int osqp_b200_device_count(void);
 
 #ifdef __cplusplus

@@ -54,7 +54,6 @@ struct TileStreamDev {
   int rows = 0, cols = 0;        // stacked rows, length of the gathered vector
   int ngroups = 0;
   int pf_chunks = 0;             // chunks (32 quads = 1280 B) a warp prefetches into L2 ahead of its register loads
-  int variant = 0;               // 0: product path; > 0: measurement variants of stream_phase (kernels.cu)
   long long nelem = 0;           // padded stream length in entries (multiple of 4)
   double *val = nullptr;         // [nelem] scaled values (zero on padding)
   unsigned short *cf = nullptr;  // [nelem] local column; bit 15 of every 4th word: row ends with this quad
@@ -206,6 +205,7 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
 int max_coop_blocks_per_sm(int block, size_t dyn_smem);
 cudaError_t configure_dyn_smem(size_t dyn_smem);
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
+cudaError_t launch_reduce_selftest(const DevPtrs &d, LaunchGeom g, double ref, double *out, cudaStream_t st);
 cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,
                                  unsigned long long *ns_out, cudaStream_t st);
 int max_active_clusters(int csize, int block, size_t dyn_smem);

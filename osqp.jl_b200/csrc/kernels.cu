@@ -176,11 +176,9 @@ __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
 // One phase of  part[group][row] = sum over the block's column group of M[row, :] vec  for the rows of every warp.
 // Must be entered by all threads of the block after a grid barrier (the previous users of the slice are done and
 // `vec` is complete and visible).
-// kD: chunks in flight per lane.  kExp != 0: measurement variants (profiles/probe_spmv.py), results are wrong:
-// 1 = no segmented scan, 2 = no gather from the staged slice, 3 = neither and no stores (loads + FMAs only).
-// kPair: the row sums go to this block's shared-memory accumulators (cluster pairs, stream_phase_paired) instead
-// of part[group][row].
-template <int kD, int kExp, bool kPair>
+// kD: chunks in flight per lane.  kPair: the row sums go to this block's shared-memory accumulators (cluster pairs,
+// stream_phase_paired) instead of part[group][row].
+template <int kD, bool kPair>
 __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int grp = __ldg(T.blk_group + b);
@@ -239,13 +237,8 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     issued++;
   };
   auto consume = [&](const QuadSlot &q) {
-    double x0, x1, x2, x3;
-    if (kExp >= 2) {
-      x0 = x1 = x2 = x3 = 1.0;
-    } else {
-      x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
-      x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
-    }
+    const double x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+    const double x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
     double inc = q.v0 * x0;
     inc = fma(q.v1, x1, inc);
     inc = fma(q.v2, x2, inc);
@@ -254,17 +247,13 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     const unsigned bal = __ballot_sync(0xffffffffu, flag);
     const unsigned below = bal & lt;
     const int h = 32 - __clz(below);  // first lane of the row this lane's quad belongs to (0 if none ended below)
-    if (kExp != 1 && kExp != 3) {
 #pragma unroll
-      for (int dlt = 1; dlt < 32; dlt <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, inc, dlt);
-        if (lane - dlt >= h) inc += t;
-      }
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const double t = __shfl_up_sync(0xffffffffu, inc, dlt);
+      if (lane - dlt >= h) inc += t;
     }
     if (below == 0u) inc += carry;  // the row started in an earlier chunk
-    if (kExp == 3) {
-      if (inc == 1.2345e300) out[0] = inc;
-    } else if (flag) {
+    if (flag) {
       if (kPair) sts_f64(out_s + 8u * (unsigned)(rdone + __popc(below)), inc);
       else out[rdone + __popc(below)] = inc;
     }
@@ -289,13 +278,7 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
 }
 
 __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
-  switch (T.variant) {
-    case 1: stream_phase_impl<kDepth, 1, false>(S, T, vec); break;
-    case 2: stream_phase_impl<kDepth, 2, false>(S, T, vec); break;
-    case 3: stream_phase_impl<kDepth, 3, false>(S, T, vec); break;
-    case 4: stream_phase_impl<2, 0, false>(S, T, vec); break;
-    default: stream_phase_impl<kDepth, 0, false>(S, T, vec); break;
-  }
+  stream_phase_impl<kDepth, false>(S, T, vec);
 }
 
 // Paired stream (TileStreamDev::paired): blocks 2p / 2p+1 of a cluster stream column groups 0 / 1 of the same row
@@ -306,7 +289,7 @@ __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, c
 template <typename Fin>
 __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const double *__restrict__ vec,
                                                     Fin fin) {
-  stream_phase_impl<kDepth, 0, true>(S, T, vec);
+  stream_phase_impl<kDepth, true>(S, T, vec);
   cluster_sync();
   const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
   const unsigned rank = (unsigned)b & 1u;
@@ -422,8 +405,9 @@ __device__ __forceinline__ void reduce_and_barrier(Grid &g, RedSmem &sm, double 
 // associative: bit-identical from run to run, like the fixed-order tree), scaled so that `ref` -- a positive value
 // every thread of the grid holds identically and that is within a few binary orders of the result -- sits at 2^50;
 // maxima of non-negative values use atomicMax on the bit pattern.  A block whose partial does not fit (|.| >= 2^55
-// after scaling, or not finite) raises a flag and every block then finishes through the plain two-level path on the
-// fp64 partials that are always written as well.  Three accumulator banks: call k uses bank k % 3 and block 0
+// after scaling, or not finite) raises a flag, and a sum that comes out with fewer than 36 significant bits means
+// `ref` was far too large: in both cases every block finishes through the plain two-level path on the fp64
+// partials that are always written as well.  Three accumulator banks: call k uses bank k % 3 and block 0
 // clears bank (k + 2) % 3 after the barrier of call k (its last readers finished before arriving at that barrier,
 // its next writers start after the barrier of call k + 1).
 template <int NV>
@@ -477,7 +461,13 @@ __device__ __forceinline__ void reduce_and_barrier_fx(Grid &g, RedSmem &sm, doub
     if (blockIdx.x == 0) g.facc[((g.fbank + 2) % 3) * kFxSlots + threadIdx.x] = 0ull;
   }
   __syncthreads();
-  if (sm.fx[kFxSlots - 1] != 0ull) {  // uniform: somebody's partial did not fit
+  bool fallback = sm.fx[kFxSlots - 1] != 0ull;  // somebody's partial did not fit
+#pragma unroll
+  for (int k = 0; k < NV; k++) {  // or `ref` was far too large: fewer than 36 significant bits in a sum
+    const long long t = (long long)sm.fx[k];
+    if (!(maxmask & (1u << k)) && (t < 0 ? -t : t) < (1ll << 36)) fallback = true;
+  }
+  if (fallback) {  // uniform over the grid: every block read the same accumulators
     for (int k = warp; k < NV; k += nwarps) {
       const double *src = g.red + ((size_t)g.bank * kRedSlots + k) * g.nblocks;
       const bool ismax = maxmask & (1u << k);
@@ -1575,6 +1565,24 @@ __global__ void __launch_bounds__(kThreads, 1) barrier_bench_kernel(const DevPtr
   }
 }
 
+// Self-test of the two cross-block reductions (tests/test_engine_parity.py): every thread contributes its global
+// index + 1 to a sum and a max; out = {tree sum, tree max, fixed-point sum, fixed-point max}.  A `ref` that is far
+// too small makes the scaled partials overflow, which must route reduce_and_barrier_fx through its fp64 fallback.
+__global__ void __launch_bounds__(kThreads, 1) reduce_selftest_kernel(const DevPtrs d, double ref, double *out) {
+  __shared__ RedSmem sm;
+  Grid g;
+  grid_init(g, d);
+  const double mine = (double)(blockIdx.x * blockDim.x + threadIdx.x + 1);
+  double a[2] = {mine, mine}, b[2] = {mine, mine};
+  reduce_and_barrier<2>(g, sm, a, 0x2u);
+  reduce_and_barrier_fx<2>(g, sm, b, 0x2u, ref);
+  double c[2] = {0.5 * mine, mine};
+  reduce_and_barrier_fx<2>(g, sm, c, 0x2u, ref);  // a second call: bank rotation
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    out[0] = a[0]; out[1] = a[1]; out[2] = b[0]; out[3] = b[1]; out[4] = c[0]; out[5] = c[1];
+  }
+}
+
 // ------------------------------------------------------------------ setup kernels (row a2, a3): simple grid-stride
 __device__ __forceinline__ double limit_scaling(double a) {
   a = a < kMinScaling ? 1.0 : a;
@@ -1915,6 +1923,12 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
     return cudaGetLastError();
   }
   return coop_launch(spmv_stream_kernel, d.bar, g, st, d, which, in, out, sigma);
+}
+
+cudaError_t launch_reduce_selftest(const DevPtrs &d, LaunchGeom g, double ref, double *out, cudaStream_t st) {
+  g.dyn_smem = 0;
+  g.cluster = 1;
+  return coop_launch(reduce_selftest_kernel, d.bar, g, st, d, ref, out);
 }
 
 cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,

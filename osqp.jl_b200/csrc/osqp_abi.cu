@@ -439,7 +439,6 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
 }
 
 c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
-  t.variant = env_int("OSQP_B200_STREAM_VARIANT", 0);
   t.rows = h.rows; t.cols = h.cols; t.ngroups = h.ngroups; t.nelem = h.nelem;
   t.split = h.split; t.srows = h.srows;
   t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 8))) & ~3;
@@ -742,6 +741,23 @@ c_int osqp_b200_cluster_probe(OSQPWorkspace *work, c_int csize) {
   Engine &e = *E(work);
   DeviceGuard guard(e.device);
   return max_active_clusters((int)csize, e.geom.block, e.geom.dyn_smem);
+}
+
+// Cross-block reductions of the persistent grid on known data (kernels.cu reduce_selftest_kernel): out[6] =
+// {tree sum, tree max, fixed-point sum, fixed-point max, second fixed-point sum, max}.
+c_int osqp_b200_reduce_selftest(OSQPWorkspace *work, c_float ref, c_float *out) {
+  if (!work || !out) return 1;
+  Engine &e = *E(work);
+  DeviceGuard guard(e.device);
+  double *dout = nullptr;
+  CU_OK(cudaMalloc(&dout, 8 * sizeof(double)));
+  cudaError_t err = launch_reduce_selftest(e.d, e.geom, ref, dout, e.stream);
+  if (err == cudaSuccess) err = cudaMemcpyAsync(out, dout, 6 * sizeof(double), cudaMemcpyDeviceToHost, e.stream);
+  if (err == cudaSuccess) err = cudaStreamSynchronize(e.stream);
+  cudaFree(dout);
+  e.h_state->needs_refresh = 1;
+  CU_OK(err);
+  return 0;
 }
 
 c_int osqp_b200_device_count(void) {

@@ -296,3 +296,26 @@ def test_infeasibility_detected_at_stream_size(pkg, engine_lib, oracle_lib):
     assert e.info.status == o.info.status == "Dual_infeasible", (e.info.status, o.info.status)
     dx = e.dual_inf_cert  # workspace.delta_x, src/interface.jl:203-209
     assert abs(dx[7]) == np.max(np.abs(dx)) and q @ dx < 0
+
+
+def test_grid_reductions_tree_fixed_point_and_fallback(pkg, engine_lib):
+    # the two cross-block reductions of the persistent kernel on known data; 148 blocks x 512 threads
+    lib = pkg.load_library(engine_lib)
+    lib.osqp_b200_reduce_selftest.restype = C.c_longlong
+    lib.osqp_b200_reduce_selftest.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
+    prob = random_qp(30000, 45000, 0.001, 45)  # big enough for the full grid
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, verbose=False)
+    prof = pkg.types.B200Profile()
+    assert lib.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
+    nthreads = int(prof.grid) * int(prof.block)
+    want_sum, want_max = nthreads * (nthreads + 1) / 2.0, float(nthreads)
+    for ref in (want_sum, 1.0, 1e-300, 1e300):  # well scaled | 2^31 off (overflow -> fallback) | absurd | absurd
+        out = (C.c_double * 6)()
+        assert lib.osqp_b200_reduce_selftest(mdl.workspace, ref, out) == 0
+        assert out[0] == want_sum and out[1] == want_max          # fp64 tree
+        assert out[3] == want_max and out[5] == want_max          # maxima are exact on either path
+        # integer data: exact on the fixed-point path and on the fp64 fallback alike
+        assert out[2] == want_sum, (ref, out[2], want_sum)
+        assert out[4] == 0.5 * want_sum, (ref, out[4])
+    mdl.clean()
