@@ -878,9 +878,12 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   }
   const int max_grid = std::min(kMaxBlocks, prop.multiProcessorCount * std::min(per_sm, env_int("OSQP_B200_BLOCKS_PER_SM", 1)));
   const long long work = 2 * nnzA + nnzP + 4LL * (n + m);
-  long long want = (work + 16383) / 16384;
+  // measured on B200 (profiles/latency_small.py): one block up to a few thousand units of work, then about one block
+  // per 3k units -- the CSR products of small problems are latency-bound and scale with the number of blocks until
+  // the grid barrier (1.5 us) takes over
+  long long want = (work + 3071) / 3072;
   int grid = (int)std::max(1LL, std::min<long long>(want, max_grid));
-  grid = env_int("OSQP_B200_GRID", grid);
+  if (env_int("OSQP_B200_GRID", 0) > 0) grid = env_int("OSQP_B200_GRID", grid);
   e.geom.grid = std::max(1, std::min(grid, max_grid));
   d.A.rows = m; d.A.cols = n; d.A.nnz = nnzA;
   d.At.rows = n; d.At.cols = m; d.At.nnz = nnzA;
