@@ -441,7 +441,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
 c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
   t.rows = h.rows; t.cols = h.cols; t.ngroups = h.ngroups; t.nelem = h.nelem;
   t.split = h.split; t.srows = h.srows;
-  t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 8))) & ~3;
+  t.pf_chunks = std::max(0, std::min(32, env_int("OSQP_B200_PF", 4))) & ~3;
   CU_OK(dalloc(e, &t.val, (size_t)h.nelem + 8));
   CU_OK(dalloc(e, &t.cf, (size_t)h.nelem + 8));
   CU_OK(dalloc(e, &t.from_csr, (size_t)h.nnz));

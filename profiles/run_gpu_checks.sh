@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-(timeout 300 python profiles/latency_small.py 2>&1 | tail -8)
-(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -3 gpurun_out/pytest_gpu.log
+for pf in 4 12; do echo "PF=$pf"; (OSQP_B200_PF=$pf timeout 600 python profiles/configs_full.py --lambdas 2 2>&1 | grep -E "per PCG|lasso sweep|Solved iter=25"); done
