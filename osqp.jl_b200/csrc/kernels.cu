@@ -300,6 +300,10 @@ __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDe
     const double mine = lds_f64(a), theirs = ld_dsmem_f64(a, rank ^ 1u);
     fin(r, rank ? theirs + mine : mine + theirs);  // group 0 first, as in part_sum
   }
+  // the partner may still be reading this block's accumulators: keep both blocks together until the reads are done
+  // (the grid barrier that follows every call would also guarantee it; this one makes the lifetime rule of
+  // distributed shared memory local and keeps compute-sanitizer quiet)
+  cluster_sync();
 }
 
 // ------------------------------------------------------------------ grid barrier + reductions

@@ -1,2 +1,4 @@
 mkdir -p gpurun_out
-for pf in 4 12; do echo "PF=$pf"; (OSQP_B200_PF=$pf timeout 600 python profiles/configs_full.py --lambdas 2 2>&1 | grep -E "per PCG|lasso sweep|Solved iter=25"); done
+(timeout 600 compute-sanitizer --tool racecheck --error-exitcode 3 python profiles/sanitize_driver.py 1 > gpurun_out/racecheck.log 2>&1); echo "racecheck rc=$?"; tail -4 gpurun_out/racecheck.log
+(timeout 600 compute-sanitizer --tool synccheck --error-exitcode 3 python profiles/sanitize_driver.py 1 > gpurun_out/synccheck.log 2>&1); echo "synccheck rc=$?"; tail -3 gpurun_out/synccheck.log
+(timeout 120 python profiles/profile_driver.py --solves 3 2>&1 | grep "^solve" | tail -2)
