@@ -813,6 +813,15 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   e.nnzA = nnzA;
   e.nnzPtriu = nnzPt;
 
+  const bool dbg_time = env_int("OSQP_B200_DEBUG", 0) != 0;
+  double t_mark = now_s();
+  auto mark = [&](const char *what) {
+    if (dbg_time) {
+      const double t = now_s();
+      fprintf(stderr, "[osqp_b200] setup %-28s %8.1f ms\n", what, (t - t_mark) * 1e3);
+      t_mark = t;
+    }
+  };
   // ---- host index work: A' CSR = caller's CSC; A CSR by counting sort; P full symmetric CSR
   std::vector<int> At_rowptr(n + 1), At_col(nnzA), A_rowptr(m + 1, 0), A_col(nnzA), mapA(nnzA);
   std::vector<double> A_val(nnzA);
@@ -866,6 +875,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
       }
   }
 
+  mark("CSR index work (host)");
   // ---- launch geometry
   cudaDeviceProp prop;
   CU_OK(cudaGetDeviceProperties(&prop, e.device));
@@ -941,6 +951,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     if (rc) return rc;
   }
 
+  mark("device alloc + CSR upload");
   // ---- tile streams for the hot phases (engine.cuh TileStreamDev)
   {
     d.blocked = 0;
@@ -1001,6 +1012,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     }
   }
 
+  mark("tile streams (host build + upload)");
   // ---- state, scaling (a2), rho vector (a3), preconditioner, convexity probe
   e.st.rho = std::min(std::max(e.st.rho, kRhoMin), kRhoMax);
   memset(e.h_state, 0, sizeof(DevState));
@@ -1019,6 +1031,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     return 7;
   }
 
+  mark("scaling, rho, precond, probe");
   memset(&e.info, 0, sizeof(e.info));
   update_status(e.info, OSQP_UNSOLVED);
   e.info.rho_estimate = e.st.rho;

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-(timeout 300 python profiles/batch_bench.py 2>&1 | tail -3)
-(timeout 600 python -m pytest tests/test_batch.py -m gpu -q -x 2>&1 | tail -2)
+(OSQP_B200_DEBUG=1 timeout 120 python profiles/profile_driver.py --solves 1 --spmv-reps 1 2>&1 | grep "osqp_b200\]" )
