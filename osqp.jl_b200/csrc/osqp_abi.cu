@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 using namespace osqpb200;
@@ -204,6 +205,28 @@ int env_int(const char *name, int dflt) {
   return (s && *s) ? atoi(s) : dflt;
 }
 
+// Host-side setup work (index transposition, tile-stream construction) is split over a few threads: fn(lo, hi) on
+// contiguous ranges of [0, count).  Every use below writes disjoint outputs per index, so the result does not
+// depend on the number of threads.
+int host_threads() {
+  const int forced = env_int("OSQP_B200_HOST_THREADS", 0);
+  if (forced > 0) return forced;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(16u, hw));
+}
+template <typename F>
+void par_ranges(long long count, long long min_per_thread, F fn) {
+  int T = host_threads();
+  if (count / std::max<long long>(1, min_per_thread) < T) T = (int)std::max<long long>(1, count / std::max<long long>(1, min_per_thread));
+  if (T <= 1) { fn(0LL, count); return; }
+  std::vector<std::thread> th;
+  for (int t = 0; t < T; t++) {
+    const long long lo = count * t / T, hi = count * (t + 1) / T;
+    th.emplace_back([=]() { fn(lo, hi); });
+  }
+  for (std::thread &x : th) x.join();
+}
+
 int pow2_lanes(double avg_nnz_per_row) {
   int forced = env_int("OSQP_B200_LANES", 0);
   if (forced > 0) return forced;
@@ -267,8 +290,10 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   {
     int r0 = 0;
     for (const CsrRef &M : mats) {
-      for (int r = 0; r < M.rows; r++)
-        for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) cnt[(size_t)(r0 + r) * ngroups + (*M.col)[k] / Wg]++;
+      par_ranges(M.rows, 8192, [&, r0](long long ra, long long rb) {
+        for (long long r = ra; r < rb; r++)
+          for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) cnt[(size_t)(r0 + r) * ngroups + (*M.col)[k] / Wg]++;
+      });
       r0 += M.rows;
     }
   }
@@ -419,15 +444,17 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
     int r0 = 0;
     long long k0 = 0;
     for (const CsrRef &M : mats) {
-      for (int r = 0; r < M.rows; r++)
-        for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) {
-          const int c = (*M.col)[k], g = c / Wg;
-          const int e = cursor[(size_t)(r0 + r) * ngroups + g]++;
-          const int piece = (e >> 2) / split_quads;
-          const int p = sr_start[g][T.sr_ptr[(size_t)g * (rows + 1) + r0 + r] + piece] + (e - 4 * split_quads * piece);
-          T.cf[p] = (unsigned short)(c - g * Wg);
-          T.from_csr[k0 + k] = stream_val_pos(p);
-        }
+      par_ranges(M.rows, 8192, [&, r0, k0](long long ra, long long rb) {  // rows are independent of each other
+        for (long long r = ra; r < rb; r++)
+          for (int k = (*M.rowptr)[r]; k < (*M.rowptr)[r + 1]; k++) {
+            const int c = (*M.col)[k], g = c / Wg;
+            const int e = cursor[(size_t)(r0 + r) * ngroups + g]++;
+            const int piece = (e >> 2) / split_quads;
+            const int p = sr_start[g][T.sr_ptr[(size_t)g * (rows + 1) + r0 + r] + piece] + (e - 4 * split_quads * piece);
+            T.cf[p] = (unsigned short)(c - g * Wg);
+            T.from_csr[k0 + k] = stream_val_pos(p);
+          }
+      });
       r0 += M.rows;
       k0 += (*M.rowptr)[M.rows];
     }
@@ -826,22 +853,37 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   std::vector<int> At_rowptr(n + 1), At_col(nnzA), A_rowptr(m + 1, 0), A_col(nnzA), mapA(nnzA);
   std::vector<double> A_val(nnzA);
   for (int j = 0; j <= n; j++) At_rowptr[j] = (int)Ac->p[j];
-  for (long long k = 0; k < nnzA; k++) {
-    const c_int r = Ac->i[k];
-    if (r < 0 || r >= m) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in A\n"); return 1; }
-    At_col[k] = (int)r;
-    A_rowptr[r + 1]++;
+  {
+    bool bad = false;
+    for (long long k = 0; k < nnzA; k++) {
+      const c_int r = Ac->i[k];
+      if (r < 0 || r >= m) { bad = true; break; }
+      At_col[k] = (int)r;
+    }
+    if (bad) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in A\n"); return 1; }
   }
+  // stable counting sort by row; each thread owns a range of rows and scans every entry, so the order inside a row
+  // (ascending column) and every position are those of the sequential sort
+  par_ranges(m, 4096, [&](long long r0, long long r1) {
+    for (long long k = 0; k < nnzA; k++) {
+      const int r = At_col[k];
+      if (r >= r0 && r < r1) A_rowptr[r + 1]++;
+    }
+  });
   for (int i = 0; i < m; i++) A_rowptr[i + 1] += A_rowptr[i];
   {
     std::vector<int> w(A_rowptr.begin(), A_rowptr.end() - 1);
-    for (int j = 0; j < n; j++)
-      for (c_int k = Ac->p[j]; k < Ac->p[j + 1]; k++) {
-        const int pos = w[Ac->i[k]]++;
-        A_col[pos] = j;
-        A_val[pos] = Ac->x[k];
-        mapA[k] = pos;
-      }
+    par_ranges(m, 4096, [&](long long r0, long long r1) {
+      for (int j = 0; j < n; j++)
+        for (c_int k = Ac->p[j]; k < Ac->p[j + 1]; k++) {
+          const int r = At_col[k];
+          if (r < r0 || r >= r1) continue;
+          const int pos = w[r]++;
+          A_col[pos] = j;
+          A_val[pos] = Ac->x[k];
+          mapA[k] = pos;
+        }
+    });
   }
   std::vector<int> P_rowptr(n + 1, 0), mapP1(nnzPt), mapP2(nnzPt);
   for (int j = 0; j < n; j++)
@@ -856,23 +898,28 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   std::vector<int> P_col(nnzP);
   std::vector<double> P_val(nnzP);
   {
+    // full symmetric CSR from the upper triangle, row-range ownership as above: the thread that owns row i places
+    // the entry (i, j), the one that owns row j its mirror (j, i)
     std::vector<int> w(P_rowptr.begin(), P_rowptr.end() - 1);
-    for (int j = 0; j < n; j++)
-      for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
-        const int i = (int)Pc->i[k];
-        int pos = w[i]++;
-        P_col[pos] = j;
-        P_val[pos] = Pc->x[k];
-        mapP1[k] = pos;
-        if (i != j) {
-          pos = w[j]++;
-          P_col[pos] = i;
-          P_val[pos] = Pc->x[k];
-          mapP2[k] = pos;
-        } else {
-          mapP2[k] = -1;
+    par_ranges(n, 4096, [&](long long r0, long long r1) {
+      for (int j = 0; j < n; j++)
+        for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
+          const int i = (int)Pc->i[k];
+          if (i >= r0 && i < r1) {
+            const int pos = w[i]++;
+            P_col[pos] = j;
+            P_val[pos] = Pc->x[k];
+            mapP1[k] = pos;
+            if (i == j) mapP2[k] = -1;
+          }
+          if (i != j && j >= r0 && j < r1) {
+            const int pos = w[j]++;
+            P_col[pos] = i;
+            P_val[pos] = Pc->x[k];
+            mapP2[k] = pos;
+          }
         }
-      }
+    });
   }
 
   mark("CSR index work (host)");
