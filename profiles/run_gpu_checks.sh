@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-(OSQP_B200_DEBUG=1 timeout 120 python profiles/profile_driver.py --solves 2 --spmv-reps 1 2>&1 | grep -E "setup|^solve" )
-(timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -2 gpurun_out/pytest_gpu.log
+(timeout 900 python -m pytest tests/test_engine_parity.py -m gpu -q -x -k "fresh_setup_at_stream or settings_variants" > gpurun_out/pytest_new.log 2>&1); tail -15 gpurun_out/pytest_new.log

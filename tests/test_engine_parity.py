@@ -319,3 +319,61 @@ def test_grid_reductions_tree_fixed_point_and_fallback(pkg, engine_lib):
         assert out[2] == want_sum, (ref, out[2], want_sum)
         assert out[4] == 0.5 * want_sum, (ref, out[4])
     mdl.clean()
+
+
+def test_update_equals_fresh_setup_at_stream_size(pkg, engine_lib):
+    # test/MOI_wrapper.jl:95-205 invariant (update == fresh setup, atol 1e-7) on a problem that runs on the tile
+    # streams: value updates must reach the stream copies of A, A' and P, re-equilibrated
+    rng = np.random.default_rng(61)
+    prob = random_qp(5000, 9000, 0.008, 61)
+    opts = dict(FIXED_RHO, eps_abs=1e-7, eps_rel=1e-7, check_termination=5)
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, **opts)
+    mdl.solve()
+    Pt = sp.triu(prob["P"], format="csc")
+    Pt.sort_indices()
+    A = prob["A"].tocsc()
+    A.sort_indices()
+    newP = Pt.data * (1.0 + 0.2 * rng.random(Pt.nnz))
+    idxA = np.sort(rng.choice(A.nnz, size=A.nnz // 3, replace=False)).astype(np.int64)
+    newA = A.data[idxA] * (1.0 + 0.05 * rng.standard_normal(idxA.size))
+    q2 = prob["q"] + 0.1 * rng.standard_normal(prob["q"].size)
+    l2, u2 = prob["l"] - 2.0, prob["u"] + 2.0  # wide enough for the perturbed A to stay feasible
+    # q first: like libosqp, a matrix update re-equilibrates with the CURRENT q (the cost scaling depends on it),
+    # a later q update would keep the old cost scaling and legitimately follow a different path than a fresh setup
+    mdl.update_q(q2)
+    mdl.update_bounds(l2, u2)
+    mdl.update_P(newP, None)
+    mdl.update_A(newA, idxA)
+    mdl.warm_start(x=np.zeros(5000), y=np.zeros(9000))
+    ru = mdl.solve()
+    P2 = sp.csc_matrix((newP, Pt.indices, Pt.indptr), shape=Pt.shape)
+    P2 = (P2 + sp.triu(P2, k=1).T).tocsc()
+    A2 = A.copy()
+    A2.data[idxA] = newA
+    fresh = pkg.Model(lib=engine_lib)
+    fresh.setup(P=P2, q=q2, A=A2, l=l2, u=u2, **opts)
+    rf = fresh.solve()
+    assert ru.info.status == rf.info.status == "Solved"
+    assert ru.info.iter == rf.info.iter
+    assert np.max(np.abs(ru.x - rf.x)) <= 1e-7 and np.max(np.abs(ru.y - rf.y)) <= 1e-7
+    prof = pkg.types.B200Profile()
+    lib = pkg.load_library(engine_lib)
+    assert lib.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0 and int(prof.streams) == 1
+    mdl.clean()
+    fresh.clean()
+
+
+@pytest.mark.parametrize("extra", [dict(scaling=0), dict(scaled_termination=True), dict(alpha=1.0),
+                                   dict(check_termination=0, max_iter=300), dict(rho=1.0, sigma=1e-3)])
+def test_settings_variants_at_stream_size(pkg, engine_lib, oracle_lib, extra):
+    prob = random_qp(4000, 7000, 0.01, 62)
+    opts = dict(FIXED_RHO, eps_abs=1e-5, eps_rel=1e-5, check_termination=5)
+    opts.update(extra)
+    r = solve_both(pkg, engine_lib, oracle_lib, prob, opts, oracle_pcg=True)
+    e, o = r["engine"][1], r["oracle"][1]
+    assert e.info.status == o.info.status
+    assert abs(e.info.iter - o.info.iter) <= 1, (e.info.iter, o.info.iter)
+    tol = 1e-5 if e.info.status == "Solved" else 1e-3
+    assert np.max(np.abs(e.x - o.x)) <= 10 * tol * (1 + np.max(np.abs(o.x)))
+    assert np.max(np.abs(e.y - o.y)) <= 10 * tol * (1 + np.max(np.abs(o.y)))
