@@ -256,6 +256,15 @@ def main():
     p1 = profile(mdl)
     launches = int(p1.launches - p0.launches)
     status = res.info.status
+    # SpMV phases as they run INSIDE the fused launch (block 0's device-side phase clock of the last step): the
+    # [A; P] stream incl. the vector-slice staging and the pair combine, and the A' stream
+    in_loop = {}
+    if p1.pcg_iters > 0 and p1.streams:
+        for name, k, nbytes in (("A_and_P", 0, p1.spmv_bytes_A + p1.spmv_bytes_P), ("At", 4, p1.spmv_bytes_At)):
+            us = p1.phase_us[k] / p1.pcg_iters
+            if us > 0:
+                in_loop[name] = {"us": us, "alg_GBs": nbytes / us / 1e3, "frac_of_8TBs": nbytes / us / 1e3 / 8000.0}
+        in_loop["us_per_pcg_iteration"] = sum(p1.phase_us[k] for k in range(8)) / p1.pcg_iters
 
     # ---- end to end through the public API with host buffers (e2e)
     mdl.update_settings(warm_start=True)
@@ -375,7 +384,8 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
                          "peak_source": peak_src, "traffic": traffic,
                          "alg_bytes_per_launch": alg_bytes / args.steps, "launch_ms": kern_ms / args.steps,
-                         "pcg_iters_per_admm_iter": pcg / max(1.0, float(iters)), "spmv": spmv},
+                         "pcg_iters_per_admm_iter": pcg / max(1.0, float(iters)), "spmv_in_loop": in_loop,
+                         "spmv_standalone_launch": spmv},
             "cpu_baseline": cpu,
             "batch": batch_line,
             "clocks": clocks,
