@@ -72,7 +72,7 @@ def test_portfolio_with_polish(pkg, engine_lib, oracle_lib, n_assets, k):
     x = e.x[:n_assets]
     assert abs(np.sum(x) - 1.0) <= 1e-3 and np.min(x) >= -1e-3 and np.max(x) <= 1 + 1e-3
     # polishing must not make the point worse than the ADMM iterate (libosqp accepts it only if residuals improve)
-    assert e.info.status_polish in (1, -1, 0)
+    assert e.info.status_polish == o.info.status_polish  # 1 at 500 assets, -1 (rejected) at 4000: same on both
     if e.info.status_polish == 1:
         assert e.info.pri_res <= 1e-6 and e.info.dua_res <= 1e-5
         assert np.max(np.abs(e.x - o.x)) <= 1e-3 * (1 + np.max(np.abs(o.x)))
