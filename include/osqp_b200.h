@@ -34,8 +34,8 @@ typedef struct {
   /* last solve: wall time (us) thread block 0 spent per phase class of the admm_kernel launch.
    * PCG iteration: 0 stream [A;P]u | 1 grid barrier | 2 combine partials -> t, rho.*t, Pu | 3 reduce + barrier |
    * 4 stream A'(rho.*t) | 5 grid barrier | 6 vector recurrences | 7 reduce + barrier.  ADMM step: 8 x,z,y update,
-   * rhs vector, barriers | 9 stream A' rhs + barrier | 10 rhs/residual + reduce | 11 residual refresh (CSR path) |
-   * 12 update_info (CSR path) | 13 rho update | 14 epilogue | 15 unused */
+   * rhs vector, barriers | 9 stream A' rhs + barrier | 10 rhs/residual + reduce | 11 residual refresh |
+   * 12 update_info | 13 rho update | 14 epilogue | 15 unused */
   c_float phase_us[16];
   c_int   streams;       /* 1: the hot phases run on tile streams; 0: CSR path (small / declined problems) */
   c_int   groups_A;      /* column groups of the [A; P] stream and of the A' stream */

@@ -130,6 +130,7 @@ struct DevPtrs {
   double *sol_x = nullptr, *sol_y = nullptr;
   // tile streams for the hot phases (blocked == 0: fall back to the CSR + L1 gather path everywhere)
   int blocked = 0;
+  int info_streams = 0;          // 1: update_info and the residual refresh also run on the tile streams
   TileStreamDev SA, ST;          // [A; P] against an n-vector, A' against an m-vector
   double *Pu = nullptr;          // n: P u of the current PCG iteration
   int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged slice

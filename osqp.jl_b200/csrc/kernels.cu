@@ -51,7 +51,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // Block 0 / thread 0 attributes its wall time to phase classes (shared-memory accumulators, copied to DevInfo at exit).
 //  0 stream [A;P]  1 barrier  2 combine t,Pu (+delta)  3 reduce+barrier  4 stream A'  5 barrier  6 vector update
 //  7 reduce+barrier | 8 z,y,x update + rhs vector + barrier  9 stream A' rhs + barrier  10 rhs/residual + reduce
-//  11 residual refresh (CSR path)  12 update_info (CSR path)  13 rho update  14 other
+//  11 residual refresh  12 update_info  13 rho update  14 other
 struct PhaseClock {
   double *acc;
   unsigned long long t;
@@ -889,6 +889,90 @@ __device__ __noinline__ void compute_info(Grid &g, RedSmem &sm, const DevPtrs &d
   S.dua_res = unscale ? cost_cinv * S.dua_t : S.dua_t;
 }
 
+// The same scalars on the tile streams (problems large enough to have them): four stream phases -- [A; P] x, A' y,
+// [A; P] dx, A' dy -- leave the six products in PCG scratch vectors that are free between two solves (t, Ap: m;
+// p, s, w, uu: n), then the owners form the 23 scalars.  Must be entered after a grid barrier that made xv, zv, yv,
+// dx and dy visible.
+__device__ __noinline__ void compute_info_stream(Grid &g, RedSmem &sm, Slice &SG, const DevPtrs &d, const SolveCfg &c,
+                                                 double cost_c, double cost_cinv, const double *xv, const double *zv,
+                                                 const double *yv, int m0, int m1, int n0, int n1, InfoScalars &S) {
+  const int tid = threadIdx.x, nth = blockDim.x, m = d.m;
+  const bool unscale = c.scaling && !c.scaled_termination;
+  auto products = [&](const double *vn, const double *vm, double *outA, double *outP, double *outT) {
+    // outA = A vn (m), outP = P vn (n), outT = A' vm (n)
+    if (d.SA.paired) {
+      stream_phase_paired(SG, d.SA, vn, [&](int r, double sum) {
+        if (r < m) outA[r] = sum;
+        else outP[r - m] = sum;
+      });
+    } else {
+      stream_phase(SG, d.SA, vn);
+      grid_barrier(g);
+      for (int i = m0 + tid; i < m1; i += nth) outA[i] = part_sum(d.SA, i);
+      for (int j = n0 + tid; j < n1; j += nth) outP[j] = part_sum(d.SA, m + j);
+    }
+    grid_barrier(g);
+    if (m > 0) {
+      stream_phase(SG, d.ST, vm);
+      grid_barrier(g);
+      for (int j = n0 + tid; j < n1; j += nth) outT[j] = part_sum(d.ST, j);
+      grid_barrier(g);  // the partials are rewritten by the next A' phase
+    }
+  };
+  products(xv, yv, d.t, d.p, d.w);
+  products(d.dx, d.dy, d.Ap, d.s, d.uu);
+  double v[23];
+#pragma unroll
+  for (int k = 0; k < 23; k++) v[k] = 0.0;
+  v[8] = -INFINITY;
+  v[9] = -INFINITY;
+  for (int row = m0 + tid; row < m1; row += nth) {
+    const double Ax = d.t[row], Adx = d.Ap[row];
+    const double zi = zv[row], ei = unscale ? d.Einv[row] : 1.0, Ei = unscale ? d.E[row] : 1.0;
+    const double li = d.l[row], ui = d.u[row], dyi = d.dy[row];
+    const double pr = fabs(Ax - zi);
+    v[0] = fmax(v[0], ei * pr);
+    v[1] = fmax(v[1], pr);
+    v[2] = fmax(v[2], ei * fabs(zi));
+    v[3] = fmax(v[3], fabs(zi));
+    v[4] = fmax(v[4], ei * fabs(Ax));
+    v[5] = fmax(v[5], fabs(Ax));
+    v[6] = fmax(v[6], Ei * fabs(dyi));
+    v[7] += ui * fmax(dyi, 0.0) + li * fmin(dyi, 0.0);
+    const double adx = ei * Adx;
+    if (ui < kInfty * kMinScaling) v[8] = fmax(v[8], adx);
+    if (li > -kInfty * kMinScaling) v[9] = fmax(v[9], -adx);
+  }
+  for (int row = n0 + tid; row < n1; row += nth) {
+    const double Px = d.p[row], Pdx = d.s[row], Aty = (m > 0) ? d.w[row] : 0.0, Atdy = (m > 0) ? d.uu[row] : 0.0;
+    const double qj = d.q[row], xj = xv[row], dxj = d.dx[row];
+    const double di = unscale ? d.Dinv[row] : 1.0, Dj = unscale ? d.D[row] : 1.0;
+    const double dr = fabs(qj + Px + Aty);
+    v[10] = fmax(v[10], di * dr);
+    v[11] = fmax(v[11], dr);
+    v[12] = fmax(v[12], di * fabs(qj));
+    v[13] = fmax(v[13], fabs(qj));
+    v[14] = fmax(v[14], di * fabs(Aty));
+    v[15] = fmax(v[15], fabs(Aty));
+    v[16] = fmax(v[16], di * fabs(Px));
+    v[17] = fmax(v[17], fabs(Px));
+    v[18] += xj * (0.5 * Px + qj);
+    v[19] = fmax(v[19], Dj * fabs(dxj));
+    v[20] += qj * dxj;
+    v[21] = fmax(v[21], di * fabs(Pdx));
+    v[22] = fmax(v[22], di * fabs(Atdy));
+  }
+  reduce_and_barrier<23>(g, sm, v, 0x7FFFFFu & ~((1u << 7) | (1u << 18) | (1u << 20)));
+  S.pri_t = v[0]; S.pri_r = v[1]; S.nz_t = v[2]; S.nz_r = v[3]; S.nAx_t = v[4]; S.nAx_r = v[5];
+  S.ndy_t = v[6]; S.lhs = v[7]; S.maxU_t = v[8]; S.maxNegL_t = v[9];
+  S.dua_t = v[10]; S.dua_r = v[11]; S.nq_t = v[12]; S.nq_r = v[13]; S.nAty_t = v[14]; S.nAty_r = v[15];
+  S.nPx_t = v[16]; S.nPx_r = v[17]; S.obj = v[18]; S.ndx_t = v[19]; S.qdx = v[20]; S.nPdx_t = v[21];
+  S.nAtdy_t = v[22];
+  S.obj_val = c.scaling ? S.obj * cost_cinv : S.obj;
+  S.pri_res = (d.m == 0) ? 0.0 : S.pri_t;
+  S.dua_res = unscale ? cost_cinv * S.dua_t : S.dua_t;
+}
+
 // Minv = 1 / (P_jj + sigma + sum_i rho_i A_ij^2) on rows [n0, n1)
 __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho_vec, double sigma, double *Minv,
                                              int n0, int n1) {
@@ -906,6 +990,39 @@ __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho
     group_reduce<1>(acc, lanesN);
     if (valid && subN == 0) Minv[row] = 1.0 / (d.Pdiag[row] + sigma + acc.a[0]);
   }
+}
+
+// Residual refresh on the tile streams: z_tilde = A x_tilde, tr = rho .* z_tilde and
+// K x_tilde = P x_tilde + sigma x_tilde + A' tr (left in d.w).  Kept out of line so that its registers do not
+// weigh on the loop body of admm_kernel.
+__device__ __noinline__ void refresh_products_stream(Grid &g, Slice &SG, const DevPtrs &d, double sigma, int m0, int m1,
+                                                     int n0, int n1) {
+  const int tid = threadIdx.x, nth = blockDim.x, m = d.m;
+  if (d.SA.paired) {
+    stream_phase_paired(SG, d.SA, d.xt, [&](int r, double sum) {
+      if (r < m) {
+        d.zt[r] = sum;
+        d.tr[r] = d.rho_vec[r] * sum;
+      } else {
+        d.Pu[r - m] = sum;
+      }
+    });
+  } else {
+    stream_phase(SG, d.SA, d.xt);
+    grid_barrier(g);
+    for (int i = m0 + tid; i < m1; i += nth) {
+      const double ti = part_sum(d.SA, i);
+      d.zt[i] = ti;
+      d.tr[i] = d.rho_vec[i] * ti;
+    }
+    for (int j = n0 + tid; j < n1; j += nth) d.Pu[j] = part_sum(d.SA, m + j);
+  }
+  grid_barrier(g);
+  if (m > 0) {
+    stream_phase(SG, d.ST, d.tr);
+    grid_barrier(g);
+  }
+  for (int j = n0 + tid; j < n1; j += nth) d.w[j] = d.Pu[j] + sigma * d.xt[j] + (m > 0 ? part_sum(d.ST, j) : 0.0);
 }
 
 // ------------------------------------------------------------------ the ADMM kernel
@@ -947,10 +1064,13 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   for (it = 1; it <= c.max_iter; it++) {
     // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde).  In steady state wv was already written by
     //         the Z phase of the previous iteration and its reduce + barrier made it visible: nothing to do here.
+    const bool refresh_on_streams = refresh && d.blocked && d.info_streams;
     if (refresh || !wv_valid) {
     for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
     wv_valid = true;
-    if (refresh && d.m > 0) {
+    if (refresh_on_streams) {
+      refresh_products_stream(g, SG, d, c.sigma, m0, m1, n0, n1);
+    } else if (refresh && d.m > 0) {
       for (int base = m0; base < m1; base += ngrpA) {
         const int row = base + grpA;
         const bool valid = row < m1;
@@ -970,8 +1090,9 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     }
     // ---- P2: b = sigma x - q + A' wv ; r = b - K x_tilde (refresh) or r += b - b_old
     double red3[3] = {0.0, 0.0, 0.0};
-    if (d.blocked && !refresh) {
-      // steady state: A' wv through the staged tiles, then the element-wise part on the owner block
+    if (d.blocked && (!refresh || refresh_on_streams)) {
+      // A' wv through the staged tiles, then the element-wise part on the owner block (a refresh rebuilds the
+      // residual from K x_tilde in d.w, the steady state carries it by recurrence)
       if (d.m > 0) {
         stream_phase(SG, d.ST, d.wv);
         stream_prefetch_head(d.SA);
@@ -981,7 +1102,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       for (int j = n0 + tid; j < n1; j += nth) {
         const double acc = (d.m > 0) ? part_sum(d.ST, j) : 0.0;
         const double bj = c.sigma * d.x[j] - d.q[j] + acc;
-        const double rj = d.r[j] + (bj - d.b[j]);
+        const double rj = refresh ? bj - d.w[j] : d.r[j] + (bj - d.b[j]);
         d.b[j] = bj;
         d.r[j] = rj;
         const double uj = d.Minv[j] * rj;
@@ -1082,7 +1203,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     can_check = c.check_termination && (it % c.check_termination == 0);
     can_print = c.verbose && ((it % kPrintInterval == 0) || it == 1);
     if (can_check || can_print) {
-      compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       pc.tick(12);
       info_iter = it;
       checks++;
@@ -1104,7 +1226,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     }
     if (c.adaptive_rho && interval && (it % interval == 0)) {
       if (!can_check && !can_print) {
-        compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+        if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
         info_iter = it;
         checks++;
       }
@@ -1128,7 +1251,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   }
   if (!can_check) {
     if (!can_print) {
-      compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       info_iter = it - 1;
       checks++;
     }

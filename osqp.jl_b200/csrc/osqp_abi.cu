@@ -1053,6 +1053,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
           return 13;
         }
         d.blocked = 1;
+        d.info_streams = env_int("OSQP_B200_INFO_STREAMS", 1) != 0;
       } else {
         e.geom.dyn_smem = 0;
       }

@@ -33,7 +33,7 @@ prob = bench.make_problem(args.n, args.m, args.density, bench.SEED)
 mdl = pkg.Model(lib=graft.LIB)
 mdl.setup(**prob, **dict(bench.SETTINGS, max_iter=args.max_iter, warm_start=False))
 PHASES = ["stream[A;P]", "barrier", "combine", "reduce+bar", "stream A'", "barrier", "vectors", "reduce+bar",
-          "admm z/y/x+bar", "admm A'rhs+bar", "admm rhs+red", "refresh(CSR)", "info(CSR)", "rho upd", "epilogue", "-"]
+          "admm z/y/x+bar", "admm A'rhs+bar", "admm rhs+red", "refresh", "update_info", "rho upd", "epilogue", "-"]
 for _ in range(args.solves):
     r = mdl.solve()
     print("solve:", r.info.status, r.info.iter, f"{r.info.solve_time * 1e3:.1f} ms")
