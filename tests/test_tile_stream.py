@@ -109,3 +109,18 @@ def test_dense_rows_are_split_into_pieces(pkg, engine_lib):
         assert np.max(np.abs(y - M @ x) / scale) < 1e-13
     rc, _, _ = _run(lib, M, x, 148, 2, paired=1)
     assert rc == 2  # split rows and cluster pairs do not combine: the builder falls back to the unpaired layout
+
+
+def test_builder_is_independent_of_host_thread_count(pkg, engine_lib, monkeypatch):
+    # osqp_setup splits its host-side index work over threads (row-range ownership): same stream, same result
+    lib = pkg.load_library(engine_lib)
+    rng = np.random.default_rng(21)
+    M = sp.random(60000, 30000, density=0.002, random_state=rng, data_rvs=rng.standard_normal, format="csr")
+    x = rng.standard_normal(30000)
+    ys = []
+    for threads in ("1", "3", "16"):
+        monkeypatch.setenv("OSQP_B200_HOST_THREADS", threads)
+        rc, y, _ = _run(lib, M, x, 148, 2)
+        assert rc == 0
+        ys.append(y)
+    assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
