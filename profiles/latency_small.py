@@ -1,3 +1,4 @@
+"""Latency of small problems on the engine (CSR path): per-solve launch cost, update cost, us per ADMM iteration."""
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np

@@ -1,3 +1,4 @@
+"""Polish outcome (status_polish, residuals, time) of the engine next to the oracle on a few problems."""
 import sys, time
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import numpy as np, ctypes as C
