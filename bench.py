@@ -9,8 +9,9 @@ start to eps_abs=eps_rel=1e-4 (adaptive_rho_interval=25, check_termination=25, p
           (settings.warm_start=0 makes the kernel cold-start itself; no input crosses PCIe)
   e2e   : same metric through the public API with HOST buffers every step:
           Model.update(q,l,u) + Model.warm_start(x0,y0) (H2D) + Model.solve() (D2H of x*, y*, info)
-  N > 1 : one process per GPU (torchrun), one independent QP per rank (seed+rank), no collective in
-          the loop; value = sum of iterations over ranks / max time over ranks ("weak" scaling).
+  N > 1 : one process per GPU (torchrun), one independent copy of the QP per rank (same seed, so the work per
+          GPU is exactly that of N = 1), no collective in the loop; value = sum of iterations over ranks / max
+          time over ranks ("weak" scaling).
 
 `--impl reference` times the CPU stand-in for the reference's libosqp path (the oracle port, reduced-KKT
 PCG backend on all host cores -- the direct LDL' of a 150k KKT with this pattern does not fit)
@@ -171,7 +172,7 @@ def main():
     workload = (f"random sparse QP n={args.n} m={args.m} density={args.density:g} fp64 (SURVEY 8d C2), "
                 f"eps=1e-4, adaptive_rho_interval=25, cold-start solve per step")
     config = {"workload": workload, "n": args.n, "m": args.m, "seed": SEED,
-              "parallelism": f"{world} independent QP(s), one per GPU, no collectives in the loop"}
+              "parallelism": f"{world} independent replica(s) of the QP, one per GPU, no collectives in the loop"}
 
     if rank == 0 or not os.path.exists(graft.LIB):
         graft.build()  # under torchrun the other ranks use what rank 0 built (or what travelled with the snapshot)
@@ -213,7 +214,7 @@ def main():
         assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(p)) == 0
         return p
 
-    prob = make_problem(args.n, args.m, args.density, SEED + rank)
+    prob = make_problem(args.n, args.m, args.density, SEED)  # every rank solves the same QP: per-GPU work is fixed
     n, m = args.n, args.m
     mat_mb = (10.6 * (2 * prob["A"].nnz + prob["P"].nnz)) / 1e6  # 10 B per stored entry, ~6 % quad padding
     config["l2"] = (f"no flush: one K-apply streams {mat_mb:.0f} MB of matrix data (L2 = 126 MB) and every termination "
