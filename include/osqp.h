@@ -152,6 +152,53 @@ typedef struct {
   c_int         summary_printed; /* @232 */
 } OSQPWorkspace;
 
+/* ---- layout checks (compile time): sizes and offsets of src/types.jl:11-217 -------------
+ * OSQP.jl unsafe_load's these structs field by field; a compiler or edit that moves a field
+ * must not build.  (C11 / C++11; tests/test_abi_layout.py checks the Python mirror.)        */
+#include <stddef.h>
+#if defined(__cplusplus)
+#define OSQP_LAYOUT_ASSERT(cond, msg) static_assert(cond, msg)
+#else
+#define OSQP_LAYOUT_ASSERT(cond, msg) _Static_assert(cond, msg)
+#endif
+#define OSQP_LAYOUT_AT(T, f, off) OSQP_LAYOUT_ASSERT(offsetof(T, f) == (off), #T "." #f " must sit at byte " #off)
+OSQP_LAYOUT_ASSERT(sizeof(c_int) == 8 && sizeof(c_float) == 8, "c_int = Int64, c_float = Float64 (src/types.jl:5-9)");
+OSQP_LAYOUT_ASSERT(sizeof(void *) == 8, "64-bit pointers");
+OSQP_LAYOUT_ASSERT(sizeof(csc) == 56, "Ccsc is 56 bytes");
+OSQP_LAYOUT_AT(csc, nzmax, 0); OSQP_LAYOUT_AT(csc, m, 8); OSQP_LAYOUT_AT(csc, n, 16); OSQP_LAYOUT_AT(csc, p, 24);
+OSQP_LAYOUT_AT(csc, i, 32); OSQP_LAYOUT_AT(csc, x, 40); OSQP_LAYOUT_AT(csc, nz, 48);
+OSQP_LAYOUT_ASSERT(sizeof(OSQPData) == 56, "Data is 56 bytes");
+OSQP_LAYOUT_AT(OSQPData, n, 0); OSQP_LAYOUT_AT(OSQPData, m, 8); OSQP_LAYOUT_AT(OSQPData, P, 16);
+OSQP_LAYOUT_AT(OSQPData, A, 24); OSQP_LAYOUT_AT(OSQPData, q, 32); OSQP_LAYOUT_AT(OSQPData, l, 40);
+OSQP_LAYOUT_AT(OSQPData, u, 48);
+OSQP_LAYOUT_ASSERT(sizeof(OSQPSettings) == 176, "Settings is 176 bytes");
+OSQP_LAYOUT_AT(OSQPSettings, rho, 0); OSQP_LAYOUT_AT(OSQPSettings, sigma, 8); OSQP_LAYOUT_AT(OSQPSettings, scaling, 16);
+OSQP_LAYOUT_AT(OSQPSettings, adaptive_rho, 24); OSQP_LAYOUT_AT(OSQPSettings, adaptive_rho_interval, 32);
+OSQP_LAYOUT_AT(OSQPSettings, adaptive_rho_tolerance, 40); OSQP_LAYOUT_AT(OSQPSettings, adaptive_rho_fraction, 48);
+OSQP_LAYOUT_AT(OSQPSettings, max_iter, 56); OSQP_LAYOUT_AT(OSQPSettings, eps_abs, 64);
+OSQP_LAYOUT_AT(OSQPSettings, eps_rel, 72); OSQP_LAYOUT_AT(OSQPSettings, eps_prim_inf, 80);
+OSQP_LAYOUT_AT(OSQPSettings, eps_dual_inf, 88); OSQP_LAYOUT_AT(OSQPSettings, alpha, 96);
+OSQP_LAYOUT_AT(OSQPSettings, linsys_solver, 104); OSQP_LAYOUT_AT(OSQPSettings, delta, 112);
+OSQP_LAYOUT_AT(OSQPSettings, polish, 120); OSQP_LAYOUT_AT(OSQPSettings, polish_refine_iter, 128);
+OSQP_LAYOUT_AT(OSQPSettings, verbose, 136); OSQP_LAYOUT_AT(OSQPSettings, scaled_termination, 144);
+OSQP_LAYOUT_AT(OSQPSettings, check_termination, 152); OSQP_LAYOUT_AT(OSQPSettings, warm_start, 160);
+OSQP_LAYOUT_AT(OSQPSettings, time_limit, 168);
+OSQP_LAYOUT_ASSERT(sizeof(OSQPInfo) == 136, "CInfo is 136 bytes");
+OSQP_LAYOUT_AT(OSQPInfo, iter, 0); OSQP_LAYOUT_AT(OSQPInfo, status, 8); OSQP_LAYOUT_AT(OSQPInfo, status_val, 40);
+OSQP_LAYOUT_AT(OSQPInfo, status_polish, 48); OSQP_LAYOUT_AT(OSQPInfo, obj_val, 56); OSQP_LAYOUT_AT(OSQPInfo, pri_res, 64);
+OSQP_LAYOUT_AT(OSQPInfo, dua_res, 72); OSQP_LAYOUT_AT(OSQPInfo, setup_time, 80); OSQP_LAYOUT_AT(OSQPInfo, solve_time, 88);
+OSQP_LAYOUT_AT(OSQPInfo, update_time, 96); OSQP_LAYOUT_AT(OSQPInfo, polish_time, 104); OSQP_LAYOUT_AT(OSQPInfo, run_time, 112);
+OSQP_LAYOUT_AT(OSQPInfo, rho_updates, 120); OSQP_LAYOUT_AT(OSQPInfo, rho_estimate, 128);
+OSQP_LAYOUT_ASSERT(sizeof(OSQPSolution) == 16, "Solution is 16 bytes");
+OSQP_LAYOUT_AT(OSQPSolution, x, 0); OSQP_LAYOUT_AT(OSQPSolution, y, 8);
+OSQP_LAYOUT_ASSERT(sizeof(OSQPWorkspace) == 240, "Julia reads 240 bytes of Workspace");
+OSQP_LAYOUT_AT(OSQPWorkspace, data, 0); OSQP_LAYOUT_AT(OSQPWorkspace, rho_vec, 24); OSQP_LAYOUT_AT(OSQPWorkspace, x, 48);
+OSQP_LAYOUT_AT(OSQPWorkspace, delta_y, 120); OSQP_LAYOUT_AT(OSQPWorkspace, delta_x, 136);
+OSQP_LAYOUT_AT(OSQPWorkspace, settings, 184); OSQP_LAYOUT_AT(OSQPWorkspace, scaling, 192);
+OSQP_LAYOUT_AT(OSQPWorkspace, solution, 200); OSQP_LAYOUT_AT(OSQPWorkspace, info, 208);
+OSQP_LAYOUT_AT(OSQPWorkspace, timer, 216); OSQP_LAYOUT_AT(OSQPWorkspace, first_run, 224);
+OSQP_LAYOUT_AT(OSQPWorkspace, summary_printed, 232);
+
 /* ---- the 30 symbols ------------------------------------------------------
  * All return 0 on success; non-zero => Julia raises ErrorException.          */
 

@@ -123,6 +123,7 @@ class BatchModel:
         rc = self.lib.osqp_batch_solve(self._h, self._f(x), self._f(y), info)
         if rc != 0:
             raise RuntimeError("Error in OSQP batch solve")
+        self.last_x = x
         return BatchResults(x, y, info)  # rows without a solution are NaN-filled by the engine (certificates aside)
 
     def update(self, q=None, l=None, u=None):
@@ -132,7 +133,7 @@ class BatchModel:
                 a.append(None)
                 continue
             v = np.ascontiguousarray(v, dtype=np.float64).reshape(self.count, w)
-            a.append(np.clip(v, -OSQP_INFTY, OSQP_INFTY) if w == self.m and v is not q else v)
+            a.append(v if len(a) == 0 else np.clip(v, -OSQP_INFTY, OSQP_INFTY))  # q is passed as is; l, u are clamped
         if self.lib.osqp_batch_update(self._h, self._f(a[0]), self._f(a[1]), self._f(a[2])) != 0:
             raise RuntimeError("Error updating the batch")
 
@@ -170,6 +171,8 @@ def gather_sharded(local, count, world_size, rank, device="cpu"):
     import torch
     import torch.distributed as dist
 
+    if isinstance(local, BatchModel):
+        local = local.last_x
     local = np.asarray(local)
     per = -(-count // world_size)
     tail = local.shape[1:]

@@ -1162,8 +1162,8 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
     }
     if (b->fast) {
       b->smem = fast_smem_bytes(f);
-      BCU(cudaFuncSetAttribute(batch_fast_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-      BCU(cudaFuncSetAttribute(batch_fast_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+      BCU(raise_dyn_smem((const void *)batch_fast_setup_kernel, b->smem));
+      BCU(raise_dyn_smem((const void *)batch_fast_solve_kernel, b->smem));
       BCU(cudaMalloc(&b->d_pattern, pat.size() * sizeof(short)));
       BCU(cudaMemcpy(b->d_pattern, pat.data(), pat.size() * sizeof(short), cudaMemcpyHostToDevice));
       d.stride = f.stride;  // the state allocation below uses the fast layout
@@ -1173,8 +1173,8 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
     fprintf(stderr, "ERROR in osqp_batch_setup: a QP of this size (%zu B) does not fit in shared memory\n", b->smem);
     return 1;
   }
-  BCU(cudaFuncSetAttribute(batch_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-  BCU(cudaFuncSetAttribute(batch_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+  BCU(raise_dyn_smem((const void *)batch_setup_kernel, b->smem));
+  BCU(raise_dyn_smem((const void *)batch_solve_kernel, b->smem));
   BCU(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
   BCU(cudaEventCreate(&b->ev0));
   BCU(cudaEventCreate(&b->ev1));

@@ -205,6 +205,7 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
                         cudaStream_t st);
 int max_coop_blocks_per_sm(int block, size_t dyn_smem);
 cudaError_t configure_dyn_smem(size_t dyn_smem);
+cudaError_t raise_dyn_smem(const void *func, size_t bytes);  // never lowers the per-device attribute
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
 cudaError_t launch_reduce_selftest(const DevPtrs &d, LaunchGeom g, double ref, double *out, cudaStream_t st);
 cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,

@@ -17,6 +17,10 @@
 #include <math.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace osqpb200 {
 
 namespace {
@@ -538,7 +542,17 @@ __device__ __forceinline__ void group_reduce(Acc<NV> &acc, int lanes) {
   }
 }
 
+// PCG breakdown (alpha <= 0 or not finite while the residual is still above its threshold).  delta = u'Ku is a plain
+// sum of products and denom = p'Kp follows from it by the Chronopoulos-Gear recurrence: a non-positive delta, or a
+// denom that is negative by far more than the cancellation in that recurrence can explain, proves that K is not
+// positive definite -- the solve ends with Non_convex instead of carrying on with truncated directions.  Anything
+// else (stagnation at round-off level) just ends this inner solve, as before.
+__device__ __forceinline__ bool pcg_negative_curvature(double delta, double denom) {
+  return delta <= 0.0 || denom < -1e-8 * fabs(delta);
+}
+
 // ------------------------------------------------------------------ PCG on K = P + sigma I + A' diag(rho) A
+// Return value: iterations run; -(iterations + 1) when the run ended on proven negative curvature.
 // Chronopoulos-Gear single-reduction variant: 3 grid barriers per iteration
 // (after t = A u | after w = K u with delta = w.u | after the vector updates with gamma, |r|inf).
 // On entry: r, uu = Minv r are set on every n-range, gamma = r.uu and rn = |r|inf are reduced.
@@ -557,6 +571,7 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
   const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
+  bool broke = false;
   while (rn > thresh && it < max_it) {
     // ---- phase A: t = A uu, tr = rho .* t
     if (d.m > 0) {
@@ -597,15 +612,19 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
     }
     reduce_and_barrier<1>(g, sm, red1, 0u);
     const double delta = red1[0];
-    double beta, alpha;
+    double beta, denom;
     if (it == 0) {
       beta = 0.0;
-      alpha = gamma / delta;
+      denom = delta;
     } else {
       beta = gamma / gamma_old;
-      alpha = gamma / (delta - beta * gamma / a_old);
+      denom = delta - beta * gamma / a_old;
     }
-    if (!(alpha > 0.0) || !isfinite(alpha)) break;  // breakdown: p'Kp <= 0 or exact convergence
+    const double alpha = gamma / denom;
+    if (!(alpha > 0.0) || !isfinite(alpha)) {  // breakdown: p'Kp <= 0 or exact convergence
+      broke = pcg_negative_curvature(delta, denom);
+      break;
+    }
     // ---- phase V: vector recurrences
     double red2[2] = {0.0, 0.0};
     for (int j = n0 + tid; j < n1; j += nth) {
@@ -638,7 +657,7 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
     a_old = alpha;
     it++;
   }
-  return it;
+  return broke ? -(it + 1) : it;
 }
 
 // Owner-side sum of the per-group partial row sums of a tile-stream phase (fixed order).
@@ -669,6 +688,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
   const int m = d.m;
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
+  bool broke = false;
   while (rn > thresh && it < max_it) {
     // beta only needs the gammas of the previous reductions
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
@@ -744,8 +764,12 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       pc.tick(3);
     }
     const double delta = red1[0];
-    const double alpha = (it == 0) ? gamma / delta : gamma / (delta - beta * gamma / a_old);
-    if (!(alpha > 0.0) || !isfinite(alpha)) break;  // breakdown: p'Kp <= 0 or exact convergence
+    const double denom = (it == 0) ? delta : delta - beta * gamma / a_old;
+    const double alpha = gamma / denom;
+    if (!(alpha > 0.0) || !isfinite(alpha)) {  // breakdown: p'Kp <= 0 or exact convergence
+      broke = pcg_negative_curvature(delta, denom);
+      break;
+    }
     // ---- phase V
     double red2[2] = {0.0, 0.0};
     {
@@ -792,7 +816,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     a_old = alpha;
     it++;
   }
-  return it;
+  return broke ? -(it + 1) : it;
 }
 
 // ------------------------------------------------------------------ update_info (row a9) + infeasibility products (row a10)
@@ -1026,7 +1050,7 @@ __device__ __noinline__ void refresh_products_stream(Grid &g, Slice &SG, const D
 }
 
 // ------------------------------------------------------------------ the ADMM kernel
-__global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, const SolveCfg c) {
+__global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ SolveCfg c) {
   __shared__ RedSmem sm;
   __shared__ double phase_acc[kPhases];
   PhaseClock pc;
@@ -1059,7 +1083,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
   S.pri_res = S.dua_res = S.obj_val = 0.0;
   long long status = ST_UNSOLVED, info_iter = 0, cg_total = 0, cg_solves = 0, checks = 0, log_rows = 0, refreshes = 0;
   double rho_est = rho, elapsed = 0.0;
-  bool can_check = false, can_print = false, wv_valid = false;
+  bool can_check = false, can_print = false, wv_valid = false, pcg_broke = false;
   long long it;
   for (it = 1; it <= c.max_iter; it++) {
     // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde).  In steady state wv was already written by
@@ -1153,12 +1177,23 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
       // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
       // (r0 measures how far the system moved since the last solve), floored at roundoff level
       const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
-      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
-                                                 red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
-                                : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
-                                          thresh, c.pcg_max_iter, m0, m1, n0, n1);
+      int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+                          : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
+                                    thresh, c.pcg_max_iter, m0, m1, n0, n1);
+      if (ncg < 0) {  // K = P + sigma I + A' rho A has a direction of non-positive curvature (uniform over the grid)
+        ncg = -ncg - 1;
+        pcg_broke = true;
+      }
       cg_total += ncg;
       cg_solves++;
+    }
+    if (pcg_broke) {
+      status = ST_NON_CVX;
+      info_iter = it;
+      can_check = true;  // nothing left to evaluate: the iterate is meaningless
+      can_print = false;
+      break;
     }
     // ---- Z: x, z, y updates (rows a6-a8); dy is stored already projected on the polar of the
     //         recession cone of [l,u] (is_primal_infeasible does that projection in place)
@@ -1259,7 +1294,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
     const long long s2 = check_termination(S, c, d.m, cost_c, cost_cinv, false);
     if (s2 != ST_UNSOLVED) status = s2;
   }
-  rho_est = rho_estimate(S, rho);
+  rho_est = pcg_broke ? rho : rho_estimate(S, rho);
   if (status == ST_UNSOLVED) {
     const long long s2 = check_termination(S, c, d.m, cost_c, cost_cinv, true);
     status = (s2 != ST_UNSOLVED) ? s2 : ST_MAX_ITER;
@@ -1327,7 +1362,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const DevPtrs d, cons
 // run CG on (P + sigma I) v = b for a pseudo-random b: CG's pivots p'(P+sigma I)p are the pivots
 // of the Lanczos tridiagonal, so a non-positive one appears as soon as the smallest Ritz value
 // crosses zero (exact after n steps; extreme eigenvalues converge first).
-__global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const DevPtrs d, double sigma, int max_it) {
+__global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const __grid_constant__ DevPtrs d, double sigma, int max_it) {
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
@@ -1394,7 +1429,8 @@ __global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const DevPtrs d, 
 // the PCG above (rho := penalty on active rows, 0 elsewhere).  libosqp factorises the
 // delta-regularised KKT and applies `polish_refine_iter` refinement steps; both converge to
 // the same KKT point of the active-set QP.
-__global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, const PolishCfg c, const SolveCfg sc,
+__global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_constant__ DevPtrs d, const __grid_constant__ PolishCfg c,
+                                                         const __grid_constant__ SolveCfg sc,
                                                          PolishOut *out) {
   __shared__ RedSmem sm;
   __shared__ double phase_acc[kPhases];
@@ -1476,10 +1512,13 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const DevPtrs d, co
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
-    cg_total += d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
-                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
-                          : pcg_run(g, sm, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0], red3[1],
-                                    thresh, c.pcg_max_iter, m0, m1, n0, n1);
+    {
+      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
+                                                 red3[0], red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+                                : pcg_run(g, sm, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
+                                          red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1);
+      cg_total += ncg < 0 ? -ncg - 1 : ncg;
+    }
     // multiplier step on active rows: y += penalty (A x - b)
     for (int i = m0 + tid; i < m1; i += nth)
       if (d.pol_rho[i] > 0.0) d.pol_y[i] += d.pol_rho[i] * (d.pol_z[i] - d.pol_b[i]);
@@ -1577,7 +1616,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_kernel(const DevPtrs d, int 
 
 // Standalone SpMV on the tile streams: exactly the phase code of pcg_run_stream (stream phase -> grid barrier ->
 // owner sum of the partials).  which 0 and 2 both run the [A; P] stream; the requested half is written out.
-__global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs d, int which, const double *in,
+__global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const __grid_constant__ DevPtrs d, int which, const double *in,
                                                                   double *out, double sigma) {
   Grid g;
   grid_init(g, d);
@@ -1621,6 +1660,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const DevPtrs 
   }
 }
 
+#ifdef OSQP_B200_DEVTOOLS  // measurement / self-test kernels: only in lib/libosqp_dev.so, never in the product
 // ------------------------------------------------------------------ stream micro-benchmark (profiles/membench.py)
 // Reads `bytes` of `buf` with the access shape of stream_phase (per lane and chunk: 2 x 16 B + 8 B loads, kD chunks in
 // flight) and nothing else, so the memory system's ceiling for that shape can be separated from the reduction code.
@@ -1710,6 +1750,8 @@ __global__ void __launch_bounds__(kThreads, 1) reduce_selftest_kernel(const DevP
     out[0] = a[0]; out[1] = a[1]; out[2] = b[0]; out[3] = b[1]; out[4] = c[0]; out[5] = c[1];
   }
 }
+
+#endif  // OSQP_B200_DEVTOOLS
 
 // ------------------------------------------------------------------ setup kernels (row a2, a3): simple grid-stride
 __device__ __forceinline__ double limit_scaling(double a) {
@@ -2053,6 +2095,7 @@ cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *o
   return coop_launch(spmv_stream_kernel, d.bar, g, st, d, which, in, out, sigma);
 }
 
+#ifdef OSQP_B200_DEVTOOLS
 cudaError_t launch_reduce_selftest(const DevPtrs &d, LaunchGeom g, double ref, double *out, cudaStream_t st) {
   g.dyn_smem = 0;
   g.cluster = 1;
@@ -2065,6 +2108,8 @@ cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int 
   g.cluster = 1;
   return coop_launch(barrier_bench_kernel, d.bar, g, st, d, iters, mode, sink, ns_out);
 }
+
+#endif  // OSQP_B200_DEVTOOLS
 
 // How many clusters of `csize` thread blocks of admm_kernel (with `dyn_smem` bytes each) can be co-resident.
 int max_active_clusters(int csize, int block, size_t dyn_smem) {
@@ -2088,6 +2133,7 @@ int max_active_clusters(int csize, int block, size_t dyn_smem) {
   return n;
 }
 
+#ifdef OSQP_B200_DEVTOOLS
 cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int depth, int grid, double *sink,
                             cudaStream_t st) {
   const char *b = reinterpret_cast<const char *>(buf);
@@ -2098,12 +2144,31 @@ cudaError_t launch_membench(const void *buf, long long bytes, int pattern, int d
   return cudaGetLastError();
 }
 
+#endif  // OSQP_B200_DEVTOOLS
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per function and per device for the whole process and the last
+// call wins: a second workspace with a smaller slice must never lower the cap under an older workspace that still
+// launches with its larger one.  The attribute is therefore only ever raised (process-wide bookkeeping per device).
+cudaError_t raise_dyn_smem(const void *func, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void *>, size_t> have;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t &cur = have[std::make_pair(dev, func)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
-  cudaError_t e = cudaFuncSetAttribute(admm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  cudaError_t e = raise_dyn_smem((const void *)admm_kernel, dyn_smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(spmv_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  e = raise_dyn_smem((const void *)spmv_stream_kernel, dyn_smem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(polish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
+  return raise_dyn_smem((const void *)polish_kernel, dyn_smem);
 }
 
 int max_coop_blocks_per_sm(int block, size_t dyn_smem) {

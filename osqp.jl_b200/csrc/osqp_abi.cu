@@ -7,6 +7,9 @@
 #include "engine.cuh"
 #include "osqp.h"
 #include "osqp_b200.h"
+#ifdef OSQP_B200_DEVTOOLS
+#include "osqp_b200_dev.h"
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -710,6 +713,7 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
   return 0;
 }
 
+#ifdef OSQP_B200_DEVTOOLS  // measurement / self-test entry points: lib/libosqp_dev.so only
 // Stream micro-benchmark (kernels.cu membench_kernel): GB/s of reading `mbytes` MB with the load shape of the
 // tile-stream phase.  pattern 0/1/2, depth = chunks in flight per lane.  Standalone: needs no workspace.
 c_float osqp_b200_membench(c_int mbytes, c_int pattern, c_int depth, c_int reps) {
@@ -787,6 +791,8 @@ c_int osqp_b200_reduce_selftest(OSQPWorkspace *work, c_float ref, c_float *out) 
   return 0;
 }
 
+#endif  // OSQP_B200_DEVTOOLS
+
 c_int osqp_b200_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
@@ -862,58 +868,107 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     }
     if (bad) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in A\n"); return 1; }
   }
-  // stable counting sort by row; each thread owns a range of rows and scans every entry, so the order inside a row
-  // (ascending column) and every position are those of the sequential sort
-  par_ranges(m, 4096, [&](long long r0, long long r1) {
-    for (long long k = 0; k < nnzA; k++) {
-      const int r = At_col[k];
-      if (r >= r0 && r < r1) A_rowptr[r + 1]++;
+  // Stable counting sort by row in O(nnz + T m): thread t takes the t-th contiguous range of columns (balanced on
+  // non-zeros), counts its entries per row into its own histogram, the histograms are turned into per-thread write
+  // cursors (row start + what the threads before it hold of that row), and every thread places its entries.  Threads
+  // are ordered like the columns, so the order inside a row (ascending column) and every position are those of the
+  // sequential sort, whatever the number of threads.
+  const int T = (int)std::max<long long>(1, std::min<long long>(host_threads(), (nnzA + nnzPt) / 65536));
+  auto col_cuts = [&](const c_int *colptr, std::vector<int> &cut) {
+    cut.assign(T + 1, n);
+    cut[0] = 0;
+    int j = 0;
+    for (int t = 1; t < T; t++) {
+      const long long target = colptr[n] * (long long)t / T;
+      while (j < n && colptr[j] < target) j++;
+      cut[t] = j;
     }
-  });
-  for (int i = 0; i < m; i++) A_rowptr[i + 1] += A_rowptr[i];
-  {
-    std::vector<int> w(A_rowptr.begin(), A_rowptr.end() - 1);
-    par_ranges(m, 4096, [&](long long r0, long long r1) {
-      for (int j = 0; j < n; j++)
+  };
+  auto run_threads = [&](auto fn) {
+    if (T == 1) { fn(0); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < T; t++) th.emplace_back([&fn, t]() { fn(t); });
+    for (std::thread &x : th) x.join();
+  };
+  // hist[t][r] -> cursors; rowptr gets the totals' prefix sum
+  auto cursors = [&](std::vector<int> &hist, int rows, std::vector<int> &rowptr) {
+    par_ranges(rows, 16384, [&](long long r0, long long r1) {
+      for (long long r = r0; r < r1; r++) {
+        int tot = 0;
+        for (int t = 0; t < T; t++) tot += hist[(size_t)t * rows + r];
+        rowptr[r + 1] = tot;
+      }
+    });
+    rowptr[0] = 0;
+    for (int r = 0; r < rows; r++) rowptr[r + 1] += rowptr[r];
+    par_ranges(rows, 16384, [&](long long r0, long long r1) {
+      for (long long r = r0; r < r1; r++) {
+        int run = rowptr[r];
+        for (int t = 0; t < T; t++) {
+          int &h = hist[(size_t)t * rows + r];
+          const int c = h;
+          h = run;
+          run += c;
+        }
+      }
+    });
+  };
+  if (m > 0) {
+    std::vector<int> cut, hist((size_t)T * m, 0);
+    col_cuts(Ac->p, cut);
+    run_threads([&](int t) {
+      int *h = hist.data() + (size_t)t * m;
+      for (long long k = Ac->p[cut[t]]; k < Ac->p[cut[t + 1]]; k++) h[At_col[k]]++;
+    });
+    cursors(hist, m, A_rowptr);
+    run_threads([&](int t) {
+      int *h = hist.data() + (size_t)t * m;
+      for (int j = cut[t]; j < cut[t + 1]; j++)
         for (c_int k = Ac->p[j]; k < Ac->p[j + 1]; k++) {
-          const int r = At_col[k];
-          if (r < r0 || r >= r1) continue;
-          const int pos = w[r]++;
+          const int pos = h[At_col[k]]++;
           A_col[pos] = j;
           A_val[pos] = Ac->x[k];
           mapA[k] = pos;
         }
     });
   }
+  // full symmetric CSR of P from the upper triangle, same scheme: entry (i, j) of column j goes to row i and, off the
+  // diagonal, its mirror (j, i) to row j; rows come out sorted by column
   std::vector<int> P_rowptr(n + 1, 0), mapP1(nnzPt), mapP2(nnzPt);
-  for (int j = 0; j < n; j++)
-    for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
-      const c_int i = Pc->i[k];
-      if (i < 0 || i >= n) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in P\n"); return 1; }
-      P_rowptr[i + 1]++;
-      if (i != j) P_rowptr[j + 1]++;
-    }
-  for (int j = 0; j < n; j++) P_rowptr[j + 1] += P_rowptr[j];
-  const long long nnzP = P_rowptr[n];
-  std::vector<int> P_col(nnzP);
-  std::vector<double> P_val(nnzP);
   {
-    // full symmetric CSR from the upper triangle, row-range ownership as above: the thread that owns row i places
-    // the entry (i, j), the one that owns row j its mirror (j, i)
-    std::vector<int> w(P_rowptr.begin(), P_rowptr.end() - 1);
-    par_ranges(n, 4096, [&](long long r0, long long r1) {
-      for (int j = 0; j < n; j++)
+    bool bad = false;
+    for (long long k = 0; k < nnzPt && !bad; k++) bad = Pc->i[k] < 0 || Pc->i[k] >= n;
+    if (bad) { fprintf(stderr, "ERROR in osqp_setup: row index out of range in P\n"); return 1; }
+  }
+  std::vector<int> P_col;
+  std::vector<double> P_val;
+  {
+    std::vector<int> cut, hist((size_t)T * n, 0);
+    col_cuts(Pc->p, cut);
+    run_threads([&](int t) {
+      int *h = hist.data() + (size_t)t * n;
+      for (int j = cut[t]; j < cut[t + 1]; j++)
         for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
           const int i = (int)Pc->i[k];
-          if (i >= r0 && i < r1) {
-            const int pos = w[i]++;
-            P_col[pos] = j;
-            P_val[pos] = Pc->x[k];
-            mapP1[k] = pos;
-            if (i == j) mapP2[k] = -1;
-          }
-          if (i != j && j >= r0 && j < r1) {
-            const int pos = w[j]++;
+          h[i]++;
+          if (i != j) h[j]++;
+        }
+    });
+    cursors(hist, n, P_rowptr);
+    P_col.resize(P_rowptr[n]);
+    P_val.resize(P_rowptr[n]);
+    run_threads([&](int t) {
+      int *h = hist.data() + (size_t)t * n;
+      for (int j = cut[t]; j < cut[t + 1]; j++)
+        for (c_int k = Pc->p[j]; k < Pc->p[j + 1]; k++) {
+          const int i = (int)Pc->i[k];
+          int pos = h[i]++;
+          P_col[pos] = j;
+          P_val[pos] = Pc->x[k];
+          mapP1[k] = pos;
+          mapP2[k] = -1;
+          if (i != j) {
+            pos = h[j]++;
             P_col[pos] = i;
             P_val[pos] = Pc->x[k];
             mapP2[k] = pos;
@@ -921,6 +976,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
         }
     });
   }
+  const long long nnzP = P_rowptr[n];
 
   mark("CSR index work (host)");
   // ---- launch geometry
@@ -1106,10 +1162,30 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   return 0;
 }
 
-c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
+static c_int solve_impl(Engine &e);
+
+// The reference ignores osqp_solve's return value (src/interface.jl:170-175) and reads info / solution straight from
+// the workspace.  libosqp cannot fail between a successful setup and the end of a solve; a GPU engine can (launch
+// refused, sticky CUDA error), so every error exit leaves an unmistakably unsolved workspace behind: status
+// Unsolved, iter 0, NaN solution -- never the results of the previous solve.
+c_int osqp_solve(OSQPWorkspace *work) {
   if (!work) { fprintf(stderr, "ERROR in osqp_solve: workspace not initialized\n"); return 1; }
   Engine &e = *E(work);
   DeviceGuard guard(e.device);
+  const c_int rc = solve_impl(e);
+  if (rc != 0) {
+    update_status(e.info, OSQP_UNSOLVED);
+    e.info.iter = 0;
+    e.info.status_polish = 0;
+    e.info.obj_val = e.info.pri_res = e.info.dua_res = NAN;
+    for (int j = 0; j < e.d.n; j++) e.h_sol_x[j] = NAN;
+    for (int i = 0; i < e.d.m; i++) e.h_sol_y[i] = NAN;
+    e.h_state->needs_refresh = 1;
+  }
+  return rc;
+}
+
+static c_int solve_impl(Engine &e) {
   if (e.clear_update_time) e.info.update_time = 0.0;
   const double t0 = now_s();
   SolveCfg c;
@@ -1127,6 +1203,20 @@ c_int osqp_solve(OSQPWorkspace *work) {  // src/interface.jl:170-175
   c.pcg_eta = e.pcg_eta; c.pcg_floor = e.pcg_floor; c.pcg_max_iter = e.pcg_max_iter;
   c.refresh_every = e.refresh_every;
   if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
+  // Automatic adaptive-rho interval (settings.adaptive_rho_interval = 0).  libosqp derives it from wall-clock:
+  // the first iteration after 0.4 * setup_time, rounded to a multiple of check_termination -- a trade between the
+  // cost of a refactorisation and of an iteration.  Here a rho update costs two stream phases, and setup_time is
+  // host index work + CUDA initialisation, unrelated to either: the rule would fire at a different iteration in
+  // every process.  The engine therefore fixes the interval deterministically at the multiple of check_termination
+  // nearest to 50 (the batched engine uses the same number); OSQP_B200_ADAPTIVE_WALLCLOCK=1 restores libosqp's rule.
+  if (e.st.adaptive_rho && e.h_state->adaptive_interval == 0 && !env_int("OSQP_B200_ADAPTIVE_WALLCLOCK", 0)) {
+    const long long N = e.st.check_termination > 0 ? e.st.check_termination : 25;
+    long long iv = ((50 + N / 2) / N) * N;
+    if (iv < N) iv = N;
+    e.h_state->adaptive_interval = iv;
+    e.st.adaptive_rho_interval = iv;
+    { c_int rc = push_state(e); if (rc) return rc; }
+  }
 
   CU_OK(cudaEventRecord(e.ev0, e.stream));
   CU_OK(launch_with_pair_fallback(e, [&]() { return launch_solve(e.d, c, e.geom, e.stream); }));

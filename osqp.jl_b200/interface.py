@@ -257,7 +257,11 @@ class Model:
             raise RuntimeError(
                 "You are trying to solve an empty model. Please setup the model before calling solve!()."
             )
-        self._lib.osqp_solve(self.workspace)  # return code ignored, :170-175
+        rc = self._lib.osqp_solve(self.workspace)  # the reference ignores the return code, :170-175
+        if rc is not None and int(rc) >= 100:
+            # engine-only failure class (100 + cudaError: launch refused, sticky device error).  libosqp has no such
+            # exit; the workspace already reads Unsolved / NaN, and this host mirror additionally refuses to go on.
+            raise RuntimeError(f"osqp_solve: CUDA failure in the engine (exit code {int(rc)})")
         workspace = self.workspace.contents
         cinfo = workspace.info.contents
         info = results.info

@@ -5,11 +5,14 @@ import scipy.sparse as sp
 
 
 def random_qp_c2(n, m, density, seed):
-    """Config 2: random sparse QP, P = S + S' + diag (diagonally dominant), two-sided feasible rows."""
+    """Config 2: random sparse QP, A = sprandn(m, n, density); P = S + S' + diag (diagonally dominant)
+    with S the strict upper triangle of sprandn(n, n, density), i.e. P holds `density` of the full n x n off the
+    diagonal: n = 50k, density 1e-3 gives nnz(A) = 5.0e6 and nnz(P_full) = 2.55e6 (triu 1.3e6), the figures of
+    SURVEY 8.  (Round 1 drew S at density / 2 -- half the P of the specification.)  Two-sided feasible rows."""
     rng = np.random.default_rng(seed)
     rvs = rng.standard_normal
     A = sp.random(m, n, density=density, random_state=rng, data_rvs=rvs, format="csc")
-    S = sp.triu(sp.random(n, n, density=density / 2, random_state=rng, data_rvs=rvs, format="csc"), k=1)
+    S = sp.triu(sp.random(n, n, density=density, random_state=rng, data_rvs=rvs, format="csc"), k=1)
     S = (S + S.T).tocsc()
     d = np.asarray(abs(S).sum(axis=1)).ravel() + rng.uniform(0.1, 1.0, n)
     P = (S + sp.diags(d)).tocsc()

@@ -4,7 +4,7 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft
-pkg = graft.load_package(); eng = pkg.load_library(graft.LIB)
+pkg = graft.load_package(); eng = pkg.load_library(graft.DEV_LIB)
 eng.osqp_b200_membench.restype = C.c_double
 eng.osqp_b200_membench.argtypes = [C.c_longlong] * 4
 for mb in (75, 1000):
@@ -16,7 +16,7 @@ for mb in (75, 1000):
 
 import bench
 prob = bench.make_problem(bench.N_VARS, bench.N_CONS, bench.DENSITY, bench.SEED)
-mdl = pkg.Model(lib=graft.LIB); mdl.setup(**prob, **bench.SETTINGS)
+mdl = pkg.Model(lib=graft.DEV_LIB); mdl.setup(**prob, **bench.SETTINGS)
 eng.osqp_b200_barrier_bench.restype = C.c_double
 eng.osqp_b200_barrier_bench.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong]
 for mode, name in ((0, "bare grid barrier"), (1, "reduce_and_barrier<2>"), (2, "barrier after scattered stores"),

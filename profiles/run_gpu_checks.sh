@@ -1,7 +1,8 @@
-# GPU validation recipe of round 1 (run under gpurun from the repo root)
+# GPU validation recipe (run under gpurun from the repo root): smoke, the GPU test-suite, the default bench line,
+# per-phase device timing of the bench workload
 mkdir -p gpurun_out
+nproc > gpurun_out/nproc.txt
 (timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3)
-(timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1); tail -2 gpurun_out/pytest_gpu.log
-(timeout 400 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err); python -c "
-import json; d=json.load(open('gpurun_out/bench.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['spmv_in_loop'], d['batch']['qp_iterations_per_sec'], d['solve']['setup_s'])"
-(timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -4)
+(timeout 1800 python -m pytest tests -m gpu -q --durations=15 > gpurun_out/pytest_gpu.log 2>&1); tail -40 gpurun_out/pytest_gpu.log
+(timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err); tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+(OSQP_B200_DEBUG=1 timeout 200 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -24)

@@ -35,6 +35,14 @@ def engine_lib():
     return graft.LIB
 
 
+@pytest.fixture(scope="session")
+def dev_lib():
+    """Development build of the engine: the product sources + measurement / self-test kernels."""
+    if not os.path.exists(graft.DEV_LIB):
+        graft.build_engine(dev=True)
+    return graft.DEV_LIB
+
+
 # Every behavioural test of the reference is run against BOTH libraries through the same
 # marshalling code: the oracle on CPU (pins the oracle), the engine on the GPU (parity).
 @pytest.fixture(params=["oracle", pytest.param("engine", marks=pytest.mark.gpu)])

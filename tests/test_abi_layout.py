@@ -67,6 +67,19 @@ def test_library_exports_every_declared_symbol(pkg, engine_lib, oracle_lib, whic
             assert hasattr(lib, sym), f"{path} does not export {sym}"
 
 
+def test_product_library_has_no_measurement_entry_points(engine_lib, dev_lib):
+    # include/osqp_b200_dev.h: the micro-benchmarks / self-tests live in lib/libosqp_dev.so only
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    dev_syms = re.findall(r"\b(osqp_[a-zA-Z0-9_]+)\s*\(", open(os.path.join(root, "include", "osqp_b200_dev.h")).read())
+    assert len(dev_syms) >= 4
+    prod, dev = C.CDLL(engine_lib), C.CDLL(dev_lib)
+    for sym in dev_syms:
+        assert not hasattr(prod, sym), f"{sym} must not ship in the product library"
+        assert hasattr(dev, sym)
+
+
 @pytest.mark.parametrize("which", ["engine", "oracle"])
 def test_default_settings(pkg, engine_lib, oracle_lib, which):
     # SURVEY Appendix A defaults; host-only call (src/types.jl:138-143)

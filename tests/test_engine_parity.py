@@ -298,8 +298,10 @@ def test_infeasibility_detected_at_stream_size(pkg, engine_lib, oracle_lib):
     assert abs(dx[7]) == np.max(np.abs(dx)) and q @ dx < 0
 
 
-def test_grid_reductions_tree_fixed_point_and_fallback(pkg, engine_lib):
-    # the two cross-block reductions of the persistent kernel on known data; 148 blocks x 512 threads
+def test_grid_reductions_tree_fixed_point_and_fallback(pkg, dev_lib):
+    # the two cross-block reductions of the persistent kernel on known data; 148 blocks x 512 threads.  The self-test
+    # kernel only exists in the development build (lib/libosqp_dev.so, -DOSQP_B200_DEVTOOLS): same sources as the product
+    engine_lib = dev_lib
     lib = pkg.load_library(engine_lib)
     lib.osqp_b200_reduce_selftest.restype = C.c_longlong
     lib.osqp_b200_reduce_selftest.argtypes = [C.c_void_p, C.c_double, C.POINTER(C.c_double)]
