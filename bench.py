@@ -362,35 +362,36 @@ def run_batch(pkg, D, total, steps, warmup, weak):
     bm.setup(Pp, Ap, Px[lo:hi], Ax[lo:hi], bq[lo:hi], bl[lo:hi], bu[lo:hi], **BATCH_SETTINGS)
     setup_s = time.perf_counter() - t0
     for _ in range(max(3, warmup)):
-        br = bm.solve()
+        br = bm.solve(copy=False)
     D.barrier()
     t0 = time.perf_counter()
     iters, kern = 0, 0.0
     for _ in range(steps):
-        br = bm.solve()  # cold start inside the kernel; x*, y*, info of every QP come back to host memory
+        br = bm.solve(copy=False)  # cold start in the kernel; x*, y*, info of every QP land in pinned host memory
         iters += int(br.iter.sum())
         kern += bm.kernel_ms
     D.barrier()
     dt = time.perf_counter() - t0
-    # e2e: every step uploads the step's q, l, u from host memory first
-    q_, l_, u_ = bq[lo:hi].copy(), bl[lo:hi].copy(), bu[lo:hi].copy()
+    # e2e: every step uploads the step's q, l, u from (pinned) host memory first
+    q_, l_, u_ = bm.input_views()
+    q_[:], l_[:], u_[:] = bq[lo:hi], np.clip(bl[lo:hi], -1e30, 1e30), np.clip(bu[lo:hi], -1e30, 1e30)
     for _ in range(2):
-        bm.update(q=q_, l=l_, u=u_); bm.solve()
+        bm.update(q=q_, l=l_, u=u_); bm.solve(copy=False)
     D.barrier()
     t0 = time.perf_counter()
     e2e_iters = 0
     for _ in range(steps):
         bm.update(q=q_, l=l_, u=u_)
-        e2e_iters += int(bm.solve().iter.sum())
+        e2e_iters += int(bm.solve(copy=False).iter.sum())
     D.barrier()
     dt_e2e = time.perf_counter() - t0
     # the only collective of the path, after the loop: every rank receives all solutions
     gather_ms, gathered = None, None
     if not weak:
-        pkg.batch.gather_sharded(bm, total, D.world, D.rank)  # warm-up (communicator, buffers)
+        pkg.batch.gather_sharded_device(bm, total, D.world, D.rank)  # warm-up (communicator, buffers)
         D.barrier()
         t0 = time.perf_counter()
-        x_all = pkg.batch.gather_sharded(bm, total, D.world, D.rank)
+        x_all = pkg.batch.gather_sharded_device(bm, total, D.world, D.rank)  # [total, n] on the device of every rank
         D.barrier()
         gather_ms, gathered = 1e3 * (time.perf_counter() - t0), int(x_all.shape[0])
     status = br.status_val

@@ -94,8 +94,17 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
 /* x_out [count][n], y_out [count][m] (NaN without a solution; for a dual / primal infeasible QP the certificate
  * delta_x / delta_y is returned in x_out / y_out), info_out [count].  Iterates stay resident for warm starts. */
 c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB200BatchInfo *info_out);
+/* The same solve without the host-side copy: *x, *y, *info point at the engine's pinned host mirrors, valid until the
+ * next call on the batch (the ownership rule of workspace->solution in the single-QP ABI, src/interface.jl:179-191). */
+c_int osqp_batch_solve_view(OSQPB200Batch *b, const c_float **x, const c_float **y, const OSQPB200BatchInfo **info);
+/* Device pointers of the last solve's x* [count][n] and y* [count][m] (valid until the next call on the batch): what a
+ * multi-GPU caller hands to its all-gather without a round trip through host memory. */
+c_int osqp_batch_device_solution(OSQPB200Batch *b, c_float **x_dev, c_float **y_dev);
 /* new q / l / u for every QP (NULL: keep); the MPC re-solve pattern of src/modcaches.jl:166-179 */
 c_int osqp_batch_update(OSQPB200Batch *b, const c_float *q, const c_float *l, const c_float *u);
+/* Pinned host staging for the inputs of osqp_batch_update: q [count][n], l, u [count][m].  A caller that writes its
+ * new data there and passes the same pointers to osqp_batch_update gets a PCIe-speed H2D without a pageable bounce. */
+c_int osqp_batch_input_view(OSQPB200Batch *b, c_float **q, c_float **l, c_float **u);
 c_int osqp_batch_warm_start(OSQPB200Batch *b, const c_float *x, const c_float *y);
 /* max_iter, eps_abs, eps_rel, eps_prim_inf, eps_dual_inf, alpha, check_termination, warm_start, scaled_termination */
 c_int osqp_batch_update_setting(OSQPB200Batch *b, const char *name, c_float value);

@@ -65,6 +65,14 @@ class BatchModel:
                                        C.POINTER(T.Settings)]
         L.osqp_batch_solve.restype = T.c_int
         L.osqp_batch_solve.argtypes = [C.c_void_p, fp, fp, C.POINTER(BatchInfo)]
+        self._has_view = hasattr(L, "osqp_batch_solve_view")  # the CUDA engine; the CPU oracle has no batch API at all
+        if self._has_view:
+            L.osqp_batch_solve_view.restype = T.c_int
+            L.osqp_batch_solve_view.argtypes = [C.c_void_p, C.POINTER(fp), C.POINTER(fp), C.POINTER(C.POINTER(BatchInfo))]
+            L.osqp_batch_input_view.restype = T.c_int
+            L.osqp_batch_input_view.argtypes = [C.c_void_p, C.POINTER(fp), C.POINTER(fp), C.POINTER(fp)]
+            L.osqp_batch_device_solution.restype = T.c_int
+            L.osqp_batch_device_solution.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
         L.osqp_batch_update.restype = T.c_int
         L.osqp_batch_update.argtypes = [C.c_void_p, fp, fp, fp]
         L.osqp_batch_warm_start.restype = T.c_int
@@ -114,9 +122,23 @@ class BatchModel:
         self.pattern_P, self.pattern_A = Pt, Ac
         return self
 
-    def solve(self):
+    def solve(self, copy=True):
+        """Solve every QP of the batch.  copy=True (default) returns private arrays, like `solve!` of the reference
+        copies `workspace.solution` out (src/interface.jl:179-191).  copy=False returns zero-copy VIEWS of the engine's
+        pinned host mirrors: valid only until the next call on this batch (solve, update, clean) -- for callers that
+        consume the result immediately and cannot afford another pass over it."""
         if not self._h:
             raise RuntimeError("You are trying to solve an empty batch. Please setup the batch before calling solve().")
+        if self._has_view and not copy:
+            px, py, pi = T.c_float_p(), T.c_float_p(), C.POINTER(BatchInfo)()
+            rc = self.lib.osqp_batch_solve_view(self._h, C.byref(px), C.byref(py), C.byref(pi))
+            if rc != 0:
+                raise RuntimeError("Error in OSQP batch solve")
+            x = np.ctypeslib.as_array(px, shape=(self.count, self.n))
+            y = (np.ctypeslib.as_array(py, shape=(self.count, self.m)) if self.m else np.empty((self.count, 0)))
+            info = C.cast(pi, C.POINTER(BatchInfo * self.count)).contents
+            self.last_x = x
+            return BatchResults(x, y, info)
         x = np.empty((self.count, self.n))
         y = np.empty((self.count, self.m))
         info = (BatchInfo * self.count)()
@@ -126,11 +148,27 @@ class BatchModel:
         self.last_x = x
         return BatchResults(x, y, info)  # rows without a solution are NaN-filled by the engine (certificates aside)
 
+    def input_views(self):
+        """(q [count, n], l [count, m], u [count, m]) numpy views of the engine's PINNED input staging.  Fill them in
+        place and pass them to update(): the H2D copy then runs at PCIe speed and no host-side copy is made."""
+        if getattr(self, "_in_views", None) is None:
+            pq, pl, pu = T.c_float_p(), T.c_float_p(), T.c_float_p()
+            if self.lib.osqp_batch_input_view(self._h, C.byref(pq), C.byref(pl), C.byref(pu)) != 0:
+                raise RuntimeError("no input staging")
+            self._in_views = (np.ctypeslib.as_array(pq, shape=(self.count, self.n)),
+                              np.ctypeslib.as_array(pl, shape=(self.count, max(self.m, 1)))[:, : self.m],
+                              np.ctypeslib.as_array(pu, shape=(self.count, max(self.m, 1)))[:, : self.m])
+        return self._in_views
+
     def update(self, q=None, l=None, u=None):
         a = []
+        views = getattr(self, "_in_views", None) or ()
         for v, w in ((q, self.n), (l, self.m), (u, self.m)):
             if v is None:
                 a.append(None)
+                continue
+            if any(v is t for t in views):  # already in pinned staging; the caller keeps |l|, |u| <= 1e30 (:107-108)
+                a.append(v)
                 continue
             v = np.ascontiguousarray(v, dtype=np.float64).reshape(self.count, w)
             a.append(v if len(a) == 0 else np.clip(v, -OSQP_INFTY, OSQP_INFTY))  # q is passed as is; l, u are clamped
@@ -153,6 +191,7 @@ class BatchModel:
         return float(self.lib.osqp_batch_last_kernel_ms(self._h))
 
     def clean(self):
+        self._in_views = None
         if self._h:
             self.lib.osqp_batch_cleanup(self._h)
             self._h = C.c_void_p()
@@ -162,6 +201,42 @@ class BatchModel:
             self.clean()
         except Exception:
             pass
+
+
+class _DeviceArray:
+    """A raw device pointer as seen by torch.as_tensor (CUDA array interface v3)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def gather_sharded_device(model, count, world_size, rank):
+    """All-gather of the last solve's x* straight from the engine's device buffer (osqp_batch_device_solution) into a
+    preallocated [count, n] device tensor on every rank: one NCCL all-gather over NVLink, no host round trip.  Shards
+    are the contiguous blocks of `shard_range`; a short last shard is padded on the device."""
+    import torch
+    import torch.distributed as dist
+
+    dx, dy = C.c_void_p(), C.c_void_p()
+    if model.lib.osqp_batch_device_solution(model._h, C.byref(dx), C.byref(dy)) != 0:
+        raise RuntimeError("no device solution")
+    per = -(-count // world_size)
+    n = model.n
+    local = torch.as_tensor(_DeviceArray(dx.value, (model.count, n)), device="cuda")
+    cache = getattr(model, "_gather_cache", None)
+    if cache is None or cache[0].shape != (world_size * per, n):
+        cache = (torch.empty((world_size * per, n), dtype=torch.float64, device="cuda"),
+                 torch.zeros((per, n), dtype=torch.float64, device="cuda"))
+        model._gather_cache = cache
+    out, pad = cache
+    if model.count != per:
+        pad[: model.count].copy_(local)
+        local = pad
+    if world_size > 1:
+        dist.all_gather_into_tensor(out, local)
+    else:
+        out.copy_(local)
+    return out[:count]
 
 
 def gather_sharded(local, count, world_size, rank, device="cpu"):

@@ -496,9 +496,9 @@ __global__ void batch_solve_kernel(BatchDims d, double *state, SolveCfg c, long 
 
 // =================================================================== fast path: one WARP per QP (n <= 32, m <= 64)
 // Lane j owns entry j of every n-vector and entries j, j + 32 of every m-vector in registers; the matrices stay sparse
-// (the shared pattern lives once per block in shared memory, each warp keeps its own values), only the Cholesky
-// factor of K is dense (row-major, ld 33: conflict-free for both substitution sweeps).  The triangular solves run on
-// warp shuffles without any block barrier, so many QPs are in flight per SM.
+// (the shared pattern lives once per block in shared memory, each warp keeps its own values), only the INVERSE of the
+// Cholesky factor of K is dense (row-major, ld 33: conflict-free by rows and by columns).  The per-iteration solve is
+// two triangular matrix-vector products without any block barrier, so many QPs are in flight per SM.
 constexpr int kFastWarps = 4;  // QPs per thread block (1 was measured: fewer resident warps, 25 % slower)
 constexpr int kLdl = 33;
 
@@ -610,39 +610,63 @@ __device__ bool fast_factor(const FastWarp &W, const FastPat &Q, const FastDims 
       for (int j = k + 1; j <= lane; j++) W.L[lane * kLdl + j] -= lik * W.L[j * kLdl + k];
     __syncwarp();
   }
-  // substitution form (fast_solve): strictly upper part zero, diagonal stored as L[k][k] - 1, rows >= n zero
-  if (ok && lane < n) {
-    for (int j = lane + 1; j < 32; j++) W.L[lane * kLdl + j] = 0.0;
-    W.L[lane * kLdl + lane] -= 1.0;
+  // Explicit inverse of the factor, in place: W.L <- L^{-1} (lower triangular, zeros above the diagonal, rows >= n
+  // zero), so that the per-iteration solve is two short matrix-vector products without a dependent chain over the
+  // columns (fast_solve).  X = L^{-1} obeys X[i][j] = -(sum_{k=j+1..i} X[i][k] L[k][j]) / L[j][j]; going through the
+  // columns from the last to the first, row i (lane i) only needs its own already inverted entries and column j of
+  // the original L, which is overwritten after every lane has read it.
+  if (ok) {
+    if (lane < n) for (int j = lane + 1; j < 32; j++) W.L[lane * kLdl + j] = 0.0;
+    __syncwarp();
+    for (int j = n - 1; j >= 0; j--) {
+      const double dj = W.invd[j];
+      double v = 0.0;
+      if (lane == j) v = dj;
+      else if (lane > j && lane < n) {
+        double a = 0.0;
+        for (int k = j + 1; k <= lane; k++) a = fma(W.L[lane * kLdl + k], W.L[k * kLdl + j], a);
+        v = -a * dj;
+      }
+      __syncwarp();
+      if (lane >= j && lane < n) W.L[lane * kLdl + j] = v;
+      __syncwarp();
+    }
   }
   __syncwarp();
   return ok;
 }
 
-// b (entry `lane` in a register) <- K^{-1} b by forward / backward substitution on warp shuffles.  `invd` is this
-// lane's 1 / L[lane][lane].  The factor is stored so that one branch-free update serves every lane: with
-// t = b_k / L_kk broadcast from lane k,  b <- b - M[lane][k] t  where M is L with zeros above the diagonal and
-// L_kk - 1 on it (lane k ends with b_k - (L_kk - 1) b_k / L_kk = b_k / L_kk, lanes above keep b).  The factor loads
-// do not depend on b, so the chain per column is one multiply, one shuffle and one fused multiply-add.
-__device__ __forceinline__ double fast_solve(const FastWarp &W, int n, double b, double invd) {
+// b (entry `lane` in a register) <- K^{-1} b = L^{-T} (L^{-1} b) with the explicit inverse factor of fast_factor:
+// t = L^{-1} b (lane j reads row j: stride kLdl, conflict-free) and x = L^{-T} t (lane j reads column j: consecutive
+// words).  The vectors go through `va` / `vb` (shared memory, broadcast reads); entries above the diagonal are stored
+// zeros, so both loops are branch-free, and each runs on four independent accumulators -- the critical path of the
+// solve is ~2 x (n / 4) fused multiply-adds instead of 2 n dependent shuffle steps of a substitution.
+__device__ __forceinline__ double fast_solve(const FastWarp &W, int n, double b, double *va, double *vb) {
   const int lane = threadIdx.x & 31;
-  const unsigned Ls = (unsigned)__cvta_generic_to_shared(W.L);
-  const unsigned Lrow = Ls + 8u * (unsigned)(lane * kLdl), Lcol = Ls + 8u * (unsigned)lane;
-#pragma unroll 6
-  for (int k = 0; k < n; k++) {
-    double lk;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lk) : "r"(Lrow + 8u * (unsigned)k));
-    const double t = __shfl_sync(0xffffffffu, b * invd, k);
-    b = fma(-lk, t, b);
+  va[lane] = lane < n ? b : 0.0;
+  __syncwarp();
+  const double *row = W.L + lane * kLdl;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int k = 0;
+  for (; k + 4 <= n; k += 4) {
+    a0 = fma(row[k], va[k], a0);
+    a1 = fma(row[k + 1], va[k + 1], a1);
+    a2 = fma(row[k + 2], va[k + 2], a2);
+    a3 = fma(row[k + 3], va[k + 3], a3);
   }
-#pragma unroll 6
-  for (int k = n - 1; k >= 0; k--) {
-    double lk;  // M'[lane][k] = M[k][lane]
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(lk) : "r"(Lcol + 8u * (unsigned)(k * kLdl)));
-    const double t = __shfl_sync(0xffffffffu, b * invd, k);
-    b = fma(-lk, t, b);
+  for (; k < n; k++) a0 = fma(row[k], va[k], a0);
+  vb[lane] = (a0 + a1) + (a2 + a3);
+  __syncwarp();
+  const double *col = W.L + lane;
+  a0 = a1 = a2 = a3 = 0.0;
+  for (k = 0; k + 4 <= n; k += 4) {
+    a0 = fma(col[k * kLdl], vb[k], a0);
+    a1 = fma(col[(k + 1) * kLdl], vb[k + 1], a1);
+    a2 = fma(col[(k + 2) * kLdl], vb[k + 2], a2);
+    a3 = fma(col[(k + 3) * kLdl], vb[k + 3], a3);
   }
-  return b;
+  for (; k < n; k++) a0 = fma(col[k * kLdl], vb[k], a0);
+  return (a0 + a1) + (a2 + a3);
 }
 
 __device__ __forceinline__ int ctype_of(double l, double u) {
@@ -798,7 +822,6 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
   long long status = ST_UNSOLVED;
   if (refactor && !fast_factor(W, Q, d, c.sigma, r0, r1)) status = ST_NON_CVX;
   __syncwarp();
-  double invd_lane = hn ? W.invd[lane] : 0.0;
   const bool unscale = c.scaling && !c.scaled_termination;
 
   InfoScalars I;
@@ -856,7 +879,8 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
       if (h1) W.vm0[i1] = r1 * z1 - y1;
       __syncwarp();
       double bj = hn ? c.sigma * x - qj + acol(Q, W.Av, W.vm0, lane, n) : 0.0;
-      const double xt = fast_solve(W, n, bj, invd_lane);
+      const double xt = fast_solve(W, n, bj, W.vn0, W.vn1);
+      __syncwarp();  // every lane is done with vn0 / vn1
       if (hn) W.vn0[lane] = xt;
       __syncwarp();
       const double zt0 = arow(Q, W.Av, W.vn0, lane, m), zt1 = arow(Q, W.Av, W.vn0, i1, m);
@@ -899,7 +923,6 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
           r0 = rho_of(t0, rho); r1 = rho_of(t1, rho); ri0 = 1.0 / r0; ri1 = 1.0 / r1;
           if (!fast_factor(W, Q, d, c.sigma, r0, r1)) { status = ST_NON_CVX; break; }
           __syncwarp();
-          invd_lane = hn ? W.invd[lane] : 0.0;
           refactor = true;
         }
       }
@@ -982,6 +1005,10 @@ struct OSQPB200Batch {
   double *stage = nullptr;  // staging for host inputs / outputs
   size_t stage_doubles = 0;
   OSQPB200BatchInfo *d_info = nullptr;
+  // pinned host mirrors of the last solve's x*, y*, info (osqp_batch_solve_view hands them out without a copy)
+  double *h_x = nullptr, *h_y = nullptr;
+  OSQPB200BatchInfo *h_info = nullptr;
+  double *h_in = nullptr;  // pinned input staging q [count][n], l, u [count][m] (osqp_batch_input_view; lazily allocated)
   int *d_fail = nullptr;
   size_t smem = 0;
   int block = 64;
@@ -1027,6 +1054,10 @@ void free_batch(OSQPB200Batch *b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   cudaFree(b->state); cudaFree(b->Pp); cudaFree(b->Pi); cudaFree(b->Ap); cudaFree(b->Ai);
   cudaFree(b->stage); cudaFree(b->d_info); cudaFree(b->d_fail); cudaFree(b->d_pattern);
+  if (b->h_x) cudaFreeHost(b->h_x);
+  if (b->h_y) cudaFreeHost(b->h_y);
+  if (b->h_info) cudaFreeHost(b->h_info);
+  if (b->h_in) cudaFreeHost(b->h_in);
   if (b->ev0) cudaEventDestroy(b->ev0);
   if (b->ev1) cudaEventDestroy(b->ev1);
   if (b->stream) cudaStreamDestroy(b->stream);
@@ -1184,6 +1215,9 @@ c_int osqp_batch_setup(OSQPB200Batch **out, c_int count, const OSQPData *pattern
   BCU(cudaMalloc(&b->Ap, (n + 1) * sizeof(long long)));
   BCU(cudaMalloc(&b->Ai, std::max<c_int>(nnzA, 1) * sizeof(long long)));
   BCU(cudaMalloc(&b->d_info, (size_t)count * sizeof(OSQPB200BatchInfo)));
+  BCU(cudaMallocHost(&b->h_x, (size_t)count * n * sizeof(double)));
+  BCU(cudaMallocHost(&b->h_y, std::max<size_t>(1, (size_t)count * m) * sizeof(double)));
+  BCU(cudaMallocHost(&b->h_info, (size_t)count * sizeof(OSQPB200BatchInfo)));
   BCU(cudaMalloc(&b->d_fail, sizeof(int)));
   BCU(cudaMemsetAsync(b->d_fail, 0, sizeof(int), b->stream));
   b->stage_doubles = (size_t)count * (size_t)(nnzP + nnzA + 2 * n + 3 * m) + 16;
@@ -1271,8 +1305,8 @@ c_int osqp_batch_warm_start(OSQPB200Batch *b, const c_float *x, const c_float *y
   return 0;
 }
 
-c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB200BatchInfo *info_out) {
-  if (!b || !x_out || !info_out) return 1;
+// One launch for the whole batch; x*, y*, info land in the pinned host mirrors (one D2H each, PCIe speed).
+static c_int batch_solve_impl(OSQPB200Batch *b) {
   DevGuard guard(b->device);
   const c_int n = b->d.n, m = b->d.m, count = b->count;
   SolveCfg c = make_cfg(b->st);
@@ -1288,14 +1322,53 @@ c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB20
                                                                           dx, dy, b->d_info);
   BCU(cudaGetLastError());
   BCU(cudaEventRecord(b->ev1, b->stream));
-  BCU(cudaMemcpyAsync(x_out, dx, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  if (m > 0 && y_out) BCU(cudaMemcpyAsync(y_out, dy, (size_t)count * m * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
-  BCU(cudaMemcpyAsync(info_out, b->d_info, (size_t)count * sizeof(OSQPB200BatchInfo), cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaMemcpyAsync(b->h_x, dx, (size_t)count * n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  if (m > 0) BCU(cudaMemcpyAsync(b->h_y, dy, (size_t)count * m * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+  BCU(cudaMemcpyAsync(b->h_info, b->d_info, (size_t)count * sizeof(OSQPB200BatchInfo), cudaMemcpyDeviceToHost, b->stream));
   BCU(cudaStreamSynchronize(b->stream));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, b->ev0, b->ev1);
   b->solve_ms = ms;
   b->bounds_changed = 0;
+  return 0;
+}
+
+c_int osqp_batch_solve(OSQPB200Batch *b, c_float *x_out, c_float *y_out, OSQPB200BatchInfo *info_out) {
+  if (!b || !x_out || !info_out) return 1;
+  const c_int rc = batch_solve_impl(b);
+  if (rc) return rc;
+  const size_t count = (size_t)b->count;
+  memcpy(x_out, b->h_x, count * b->d.n * sizeof(double));
+  if (b->d.m > 0 && y_out) memcpy(y_out, b->h_y, count * b->d.m * sizeof(double));
+  memcpy(info_out, b->h_info, count * sizeof(OSQPB200BatchInfo));
+  return 0;
+}
+
+c_int osqp_batch_solve_view(OSQPB200Batch *b, const c_float **x, const c_float **y, const OSQPB200BatchInfo **info) {
+  if (!b) return 1;
+  const c_int rc = batch_solve_impl(b);
+  if (rc) return rc;
+  if (x) *x = b->h_x;
+  if (y) *y = b->h_y;
+  if (info) *info = b->h_info;
+  return 0;
+}
+
+c_int osqp_batch_input_view(OSQPB200Batch *b, c_float **q, c_float **l, c_float **u) {
+  if (!b) return 1;
+  DevGuard guard(b->device);
+  const size_t count = (size_t)b->count, n = (size_t)b->d.n, m = (size_t)b->d.m;
+  if (!b->h_in) BCU(cudaMallocHost(&b->h_in, std::max<size_t>(1, count * (n + 2 * m)) * sizeof(double)));
+  if (q) *q = b->h_in;
+  if (l) *l = b->h_in + count * n;
+  if (u) *u = b->h_in + count * (n + m);
+  return 0;
+}
+
+c_int osqp_batch_device_solution(OSQPB200Batch *b, c_float **x_dev, c_float **y_dev) {
+  if (!b) return 1;
+  if (x_dev) *x_dev = b->stage;
+  if (y_dev) *y_dev = b->stage + (size_t)b->count * b->d.n;
   return 0;
 }
 

@@ -73,6 +73,32 @@ struct TileStreamDev {
   double *part = nullptr;        // [ngroups][srows] partial sums of the stream rows of the last phase
 };
 
+// Low-rank part of the PCG preconditioner (Woodbury).  K = P + sigma I + A' diag(rho) A is Jacobi-friendly except for
+// a FEW coupling rows of A that carry the equality weight 1e3 rho and touch many columns (budget / factor rows of a
+// portfolio, linking constraints): each puts an outlier eigenvalue into the Jacobi-scaled K and costs about one PCG
+// iteration per ADMM step.  With W = those rows (w <= kWoodMax), D = diag(P) + sigma + diag of the remaining rows and
+// S = diag(sqrt(rho_W)):
+//     M = D + A_W' S^2 A_W ,   M^{-1} = D^{-1} - D^{-1} A_W' S C^{-1} S A_W D^{-1} ,   C = I + S A_W D^{-1} A_W' S  (w x w)
+// C^{-1} is formed explicitly on the device whenever rho changes (admm_kernel / polish_kernel, kernels.cu
+// wood_refresh); applying M^{-1} costs two small products with compact copies of A_W and A_W' and one w x w product.
+constexpr int kWoodMax = 512;
+constexpr int kWoodCols = 8;   // columns of C assembled per round of wood_refresh
+
+struct WoodDev {
+  int w = 0;                 // rows in the set (0: plain Jacobi)
+  int ld = 0;                // leading dimension of C / Cinv
+  int *rows = nullptr;       // [w] row of A of member a
+  int *idx = nullptr;        // [m] member index of a row of A, -1 otherwise
+  int *rp = nullptr, *ci = nullptr, *src = nullptr;     // A_W  as CSR (w rows over the n columns); src: position in A.val
+  double *val = nullptr;
+  int *trp = nullptr, *tci = nullptr, *tsrc = nullptr;  // A_W' as CSR (n rows over the w members)
+  double *tval = nullptr;
+  double *C = nullptr, *Cinv = nullptr;  // [ld * ld] C (then its Cholesky factor), explicit inverse
+  double *s = nullptr, *t = nullptr, *g = nullptr;  // [ld] sqrt(penalty), S A_W v, S C^{-1} t
+  double *v = nullptr;       // [n] D^{-1} r
+  double *vk = nullptr;      // [kWoodCols][n + 8] scratch of wood_refresh
+};
+
 // Persistent solver state that survives between launches (device memory).
 struct DevState {
   double rho;              // current scalar rho (settings->rho)
@@ -82,7 +108,7 @@ struct DevState {
   int needs_refresh;       // PCG residual/z_tilde recurrences invalid (matrix, rho or iterate change)
   int pd_check_failed;     // setup-time curvature probe found p'(P+sigma I)p <= 0
   int ctype_changed;       // update_rho_vec saw a constraint type change
-  int pad;
+  int pd_certified;        // k_gershgorin: every row of the scaled P + sigma I is strictly diagonally dominant (=> PD)
 };
 
 // What one osqp_solve launch reports back (device -> pinned host).
@@ -132,6 +158,14 @@ struct DevPtrs {
   int blocked = 0;
   int info_streams = 0;          // 1: update_info and the residual refresh also run on the tile streams
   TileStreamDev SA, ST;          // [A; P] against an n-vector, A' against an m-vector
+  // fp32 shadows of the two vectors the PCG phases gather (u = M^{-1} r and rho .* (A u)): the staged slices of
+  // these phases are fp32 (half the L2 -> SM traffic of the staging); u is rounded BEFORE it enters the recurrences, so
+  // CG stays exact for a preconditioner perturbed at the 6e-8 level; the rounding of rho .* (A u) perturbs one K-apply
+  // by 6e-8 of that step's own residual change (kernels.cu store_u / store_tr).  Values stay fp64 and sums accumulate
+  // in fp64.  f32_slices == 0: everything fp64 (OSQP_B200_F32_SLICES=0).
+  int f32_slices = 0;
+  float *uu32 = nullptr, *tr32 = nullptr;  // n, m
+  WoodDev W;                     // low-rank part of the preconditioner (w == 0: none)
   double *Pu = nullptr;          // n: P u of the current PCG iteration
   int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged slice
   int smem_rows = 0;             // doubles of dynamic shared memory for the row sums of a cluster pair (0: unpaired)
@@ -163,6 +197,7 @@ struct SolveCfg {
   double pcg_floor;
   int pcg_max_iter;
   int refresh_every;       // recompute z_tilde = A x_tilde and r = b - K x_tilde every k ADMM iterations (1 = always)
+  int wood_refresh;        // the Woodbury data (WoodDev C^{-1}, s, D) are stale: rebuild before the first PCG
 };
 
 struct PolishCfg {
@@ -193,7 +228,8 @@ cudaError_t launch_scale_vectors(const DevPtrs &d, int do_q, int do_bounds, cuda
 cudaError_t launch_set_rho_vec(const DevPtrs &d, double rho, int detect_change_only, cudaStream_t st);
 cudaError_t launch_apply_rho(const DevPtrs &d, double rho, cudaStream_t st);
 cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st);
-cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st);
+cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, int trials, cudaStream_t st);
+cudaError_t launch_gershgorin(const DevPtrs &d, double sigma, cudaStream_t st);
 cudaError_t launch_warm_start(const DevPtrs &d, const double *x_in, const double *y_in, int scaling, cudaStream_t st);
 cudaError_t launch_cold_start(const DevPtrs &d, cudaStream_t st);
 cudaError_t launch_scatter_values(double *dst, const double *vals, const long long *idx, const int *map,
@@ -207,6 +243,7 @@ int max_coop_blocks_per_sm(int block, size_t dyn_smem);
 cudaError_t configure_dyn_smem(size_t dyn_smem);
 cudaError_t raise_dyn_smem(const void *func, size_t bytes);  // never lowers the per-device attribute
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);
+cudaError_t launch_fill_wood(const DevPtrs &d, cudaStream_t st);
 cudaError_t launch_reduce_selftest(const DevPtrs &d, LaunchGeom g, double ref, double *out, cudaStream_t st);
 cudaError_t launch_barrier_bench(const DevPtrs &d, LaunchGeom g, int iters, int mode, double *sink,
                                  unsigned long long *ns_out, cudaStream_t st);

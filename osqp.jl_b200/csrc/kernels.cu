@@ -123,6 +123,11 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
   asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
   asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
 }
@@ -182,8 +187,9 @@ __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
 // `vec` is complete and visible).
 // kD: chunks in flight per lane.  kPair: the row sums go to this block's shared-memory accumulators (cluster pairs,
 // stream_phase_paired) instead of part[group][row].
-template <int kD, bool kPair>
-__device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
+// kF32: `vec` is an array of float (the fp32 shadows DevPtrs::uu32 / tr32); the slice is staged and gathered as fp32.
+template <int kD, bool kPair, bool kF32>
+__device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T, const void *__restrict__ vec) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int grp = __ldg(T.blk_group + b);
   const unsigned parity = S.parity;
@@ -193,9 +199,9 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     // generic-proxy writes before the async-proxy (TMA) reads
     asm volatile("fence.proxy.async;" ::: "memory");
     const int col0 = __ldg(T.grp_col0 + grp), ncols = __ldg(T.grp_col0 + grp + 1) - col0;
-    const unsigned bytes = ((unsigned)ncols * 8u + 15u) & ~15u;
+    const unsigned bytes = ((unsigned)ncols * (kF32 ? 4u : 8u) + 15u) & ~15u;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.mbar), "r"(bytes) : "memory");
-    const char *g = reinterpret_cast<const char *>(vec + col0);
+    const char *g = reinterpret_cast<const char *>(vec) + (size_t)col0 * (kF32 ? 4u : 8u);
     for (unsigned off = 0; off < bytes; off += 32768u) {
       const unsigned chunk = (bytes - off < 32768u) ? (bytes - off) : 32768u;
       asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -241,8 +247,14 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     issued++;
   };
   auto consume = [&](const QuadSlot &q) {
-    const double x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)), x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
-    const double x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)), x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    double x0, x1, x2, x3;
+    if (kF32) {
+      x0 = (double)lds_f32(xs + ((q.c01 & 0x7fffu) << 2)); x1 = (double)lds_f32(xs + ((q.c01 >> 14) & 0x1fffcu));
+      x2 = (double)lds_f32(xs + ((q.c23 & 0x7fffu) << 2)); x3 = (double)lds_f32(xs + ((q.c23 >> 14) & 0x1fffcu));
+    } else {
+      x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)); x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+      x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)); x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    }
     double inc = q.v0 * x0;
     inc = fma(q.v1, x1, inc);
     inc = fma(q.v2, x2, inc);
@@ -282,7 +294,10 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
 }
 
 __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
-  stream_phase_impl<kDepth, false>(S, T, vec);
+  stream_phase_impl<kDepth, false, false>(S, T, vec);
+}
+__device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &T, const float *__restrict__ vec) {
+  stream_phase_impl<kDepth, false, true>(S, T, vec);
 }
 
 // Paired stream (TileStreamDev::paired): blocks 2p / 2p+1 of a cluster stream column groups 0 / 1 of the same row
@@ -290,10 +305,10 @@ __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, c
 // reading its partner's partial sums through distributed shared memory, and hands the complete row sum to
 // fin(stacked_row, sum).  No partial vector goes through global memory and no grid barrier is needed for the combine.
 // Every thread of both blocks must call this; the accumulators are next written after at least one grid barrier.
-template <typename Fin>
-__device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const double *__restrict__ vec,
+template <bool kF32 = false, typename Fin>
+__device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const void *__restrict__ vec,
                                                     Fin fin) {
-  stream_phase_impl<kDepth, true>(S, T, vec);
+  stream_phase_impl<kDepth, true, kF32>(S, T, vec);
   cluster_sync();
   const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
   const unsigned rank = (unsigned)b & 1u;
@@ -561,6 +576,31 @@ struct PcgVecs {
   double *r, *uu, *p, *s, *w, *t, *tr, *Ap;
 };
 
+// u = M^{-1} r and tr = rho .* (A u) as the PCG phases gather them: with fp32 slices the value is rounded to fp32 ONCE,
+// here, and the rounded value is what every recurrence and dot product sees (engine.cuh DevPtrs::f32_slices).
+__device__ __forceinline__ double store_u(const DevPtrs &d, double *uvec, int j, double u) {
+  if (d.f32_slices) {
+    const float f = (float)u;
+    d.uu32[j] = f;
+    u = (double)f;
+  }
+  uvec[j] = u;
+  return u;
+}
+__device__ __forceinline__ double store_tr(const DevPtrs &d, double *trvec, int i, double tr) {
+  if (d.f32_slices) {
+    const float f = (float)tr;
+    d.tr32[i] = f;
+    tr = (double)f;
+  }
+  trvec[i] = tr;
+  return tr;
+}
+
+// Woodbury part of the preconditioner (defined further down)
+__device__ __noinline__ double wood_apply(Grid &g, RedSmem &sm, const DevPtrs &d, const double *Dinv,
+                                          const double *rvec, double *uvec, int n0, int n1);
+
 __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const DevPtrs &d, const PcgVecs &v,
                                     const double *rho_vec,
                                     const double *Minv, double sigma, double *xvec, double *zvec, double gamma,
@@ -684,6 +724,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
                                            const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma, double *xvec,
                                            double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
                                            int m1, int n0, int n1) {
+  const bool wood = d.W.w > 0;  // Minv is then D^{-1} of the Woodbury preconditioner (wood_refresh, wood_apply)
   const int tid = threadIdx.x, nth = blockDim.x;
   const int m = d.m;
   double a_old = 1.0, gamma_old = 1.0;
@@ -696,23 +737,25 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     if (d.SA.paired) {
       // ---- phase A with the combine fused in (cluster pairs): no partials, no extra grid barrier
       const bool rec = zvec != nullptr && it > 0;
-      stream_phase_paired(S, d.SA, v.uu, [&](int r, double sum) {
+      auto fin = [&](int r, double sum) {
         if (r < m) {
-          const double tr = rho_vec[r] * sum;
+          const double tr = store_tr(d, v.tr, r, rho_vec[r] * sum);
           if (zvec != nullptr) v.Ap[r] = rec ? sum + beta * v.Ap[r] : sum;
-          v.tr[r] = tr;
           red1[0] += sum * tr;
         } else {
           const double uj = v.uu[r - m];
           d.Pu[r - m] = sum;
           red1[0] += uj * (sum + sigma * uj);
         }
-      });
+      };
+      if (d.f32_slices) stream_phase_paired<true>(S, d.SA, d.uu32, fin);
+      else stream_phase_paired<false>(S, d.SA, v.uu, fin);
       if (m > 0) stream_prefetch_head(d.ST);
       pc.tick(0);
     } else {
     // ---- phase A
-    stream_phase(S, d.SA, v.uu);
+    if (d.f32_slices) stream_phase_f32(S, d.SA, d.uu32);
+    else stream_phase(S, d.SA, v.uu);
     if (m > 0) stream_prefetch_head(d.ST);
     pc.tick(0);
     grid_barrier(g);
@@ -731,15 +774,13 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
         if (h2) { t2 = part_sum(d.SA, i2); r2 = rho_vec[i2]; if (rec) a2 = v.Ap[i2]; }
         if (hj) { pu = part_sum(d.SA, m + j); uj = v.uu[j]; }
         if (h1) {
-          const double tr = r1 * t1;
+          const double tr = store_tr(d, v.tr, i, r1 * t1);
           if (zvec != nullptr) v.Ap[i] = t1 + beta * a1;  // A p, for the z = A x recurrence (beta = 0 at it 0)
-          v.tr[i] = tr;
           red1[0] += t1 * tr;
         }
         if (h2) {
-          const double tr = r2 * t2;
+          const double tr = store_tr(d, v.tr, i2, r2 * t2);
           if (zvec != nullptr) v.Ap[i2] = t2 + beta * a2;
-          v.tr[i2] = tr;
           red1[0] += t2 * tr;
         }
         if (hj) {
@@ -754,7 +795,8 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       reduce_and_barrier_fx<1>(g, sm, red1, 0u, gamma);  // delta / gamma is a Rayleigh quotient of M^-1 K
       pc.tick(3);
       // ---- phase B
-      stream_phase(S, d.ST, v.tr);
+      if (d.f32_slices) stream_phase_f32(S, d.ST, d.tr32);
+      else stream_phase(S, d.ST, v.tr);
       stream_prefetch_head(d.SA);
       pc.tick(4);
       grid_barrier(g);
@@ -798,8 +840,9 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
           xvec[j] = xj + alpha * pj;
           rj -= alpha * sj;
           v.r[j] = rj;
-          const double un = mj * rj;
-          v.uu[j] = un;
+          double un = mj * rj;
+          if (wood) d.W.v[j] = un;
+          else un = store_u(d, v.uu, j, un);
           red2[0] += rj * un;
           red2[1] = fmax(red2[1], fabs(rj));
         }
@@ -809,6 +852,11 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     }
     pc.tick(6);
     reduce_and_barrier_fx<2>(g, sm, red2, 0x2u, gamma);
+    if (wood) {  // the low-rank correction of u = M^{-1} r and the gamma that goes with it
+      double redg[1] = {wood_apply(g, sm, d, Minv, v.r, v.uu, n0, n1)};
+      reduce_and_barrier<1>(g, sm, redg, 0u);
+      red2[0] = redg[0];
+    }
     pc.tick(7);
     gamma_old = gamma;
     gamma = red2[0];
@@ -997,9 +1045,10 @@ __device__ __noinline__ void compute_info_stream(Grid &g, RedSmem &sm, Slice &SG
   S.dua_res = unscale ? cost_cinv * S.dua_t : S.dua_t;
 }
 
-// Minv = 1 / (P_jj + sigma + sum_i rho_i A_ij^2) on rows [n0, n1)
+// Minv = 1 / (P_jj + sigma + sum_i rho_i A_ij^2) on rows [n0, n1); rows of A with skip[i] >= 0 (members of the Woodbury
+// set, engine.cuh WoodDev) are left out of the sum when `skip` is given
 __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho_vec, double sigma, double *Minv,
-                                             int n0, int n1) {
+                                             int n0, int n1, const int *skip = nullptr) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lanesN = d.At.lanes;
   const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
@@ -1008,12 +1057,173 @@ __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho
     const bool valid = row < n1;
     Acc<1> acc;
     acc.a[0] = 0.0;
-    if (d.m > 0)
-      row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
-                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += rho_vec[c] * a * a; });
+    if (d.m > 0) {
+      if (skip == nullptr)
+        row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += rho_vec[c] * a * a; });
+      else
+        row_accumulate<1>(d.At.rowptr, d.At.col, d.At.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { if (__ldg(skip + c) < 0) ac.a[0] += rho_vec[c] * a * a; });
+    }
     group_reduce<1>(acc, lanesN);
     if (valid && subN == 0) Minv[row] = 1.0 / (d.Pdiag[row] + sigma + acc.a[0]);
   }
+}
+
+// ------------------------------------------------------------------ Woodbury part of the preconditioner (engine.cuh WoodDev)
+// Sum of one value per thread over the block, fixed order (warp shuffle tree, then the warps in order).
+__device__ __forceinline__ double block_sum(RedSmem &sm, double a) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) sm.part[warp][0] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int k = 0; k < nwarps; k++) t += sm.part[k][0];
+    sm.res[0] = t;
+  }
+  __syncthreads();
+  const double r = sm.res[0];
+  __syncthreads();
+  return r;
+}
+
+// Cholesky factor of C (w x w, lower triangle, in place) and the explicit inverse Cinv = C^{-1}; ONE thread block.
+// C = I + (positive semidefinite), so the pivots are >= 1 up to rounding; a pivot that is not positive (never seen)
+// is replaced by 1, which only weakens the preconditioner.
+__device__ __noinline__ void wood_factor(const WoodDev &W) {
+  const int w = W.w, ld = W.ld, tid = threadIdx.x, nth = blockDim.x;
+  double *C = W.C, *X = W.Cinv;
+  __shared__ double dk;
+  for (int k = 0; k < w; k++) {
+    if (tid == 0) {
+      const double p = C[k * ld + k];
+      dk = p > 0.0 ? sqrt(p) : 1.0;
+      C[k * ld + k] = dk;
+    }
+    __syncthreads();
+    const double inv = 1.0 / dk;
+    for (int i = k + 1 + tid; i < w; i += nth) C[i * ld + k] *= inv;
+    __syncthreads();
+    const int R = w - k - 1;
+    for (int e = tid; e < R * R; e += nth) {
+      const int i = k + 1 + e / R, j = k + 1 + e % R;
+      if (j <= i) C[i * ld + j] -= C[i * ld + k] * C[j * ld + k];
+    }
+    __syncthreads();
+  }
+  // column a of the inverse by thread a: L y = e_a, L' x = y, in place in X[:, a]; every thread walks the same
+  // (i, k), so the factor loads are broadcasts and the X loads are coalesced
+  for (int a = tid; a < w; a += nth) {
+    for (int i = 0; i < w; i++) {
+      double acc = (i == a) ? 1.0 : 0.0;
+      for (int k = 0; k < i; k++) acc -= C[i * ld + k] * X[k * ld + a];
+      X[i * ld + a] = acc / C[i * ld + i];
+    }
+    for (int i = w - 1; i >= 0; i--) {
+      double acc = X[i * ld + a];
+      for (int k = i + 1; k < w; k++) acc -= C[k * ld + i] * X[k * ld + a];
+      X[i * ld + a] = acc / C[i * ld + i];
+    }
+  }
+  __syncthreads();
+}
+
+// Rebuild the Woodbury data for the penalty vector `pen` (rho_vec of the ADMM loop, or the polish penalties) and the
+// diagonal shift `sig`: Dinv (without the member rows), s = sqrt(pen_W), C = I + S A_W Dinv A_W' S, Cinv.  C is
+// assembled kWoodCols columns per round: the scaled member rows are scattered into dense scratch vectors and every
+// member row takes its dot products with them (one thread block per row, fixed-order block sums).
+// Entered and left by every thread of the grid; starts and ends with a grid barrier.
+__device__ __noinline__ void wood_refresh(Grid &g, RedSmem &sm, const DevPtrs &d, const double *pen, double sig,
+                                          double *Dinv, int n0, int n1) {
+  const WoodDev &W = d.W;
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x, nb = gridDim.x;
+  const int w = W.w, ld = W.ld;
+  const size_t np = (size_t)d.n + 8;
+  grid_barrier(g);  // pen is complete
+  for (int a = b * nth + tid; a < w; a += nb * nth) W.s[a] = sqrt(fmax(pen[W.rows[a]], 0.0));
+  precond_rows(d, pen, sig, Dinv, n0, n1, W.idx);
+  grid_barrier(g);
+  for (int a0 = 0; a0 < w; a0 += kWoodCols) {
+    const int nc = min(kWoodCols, w - a0);
+    for (int c = 0; c < nc; c++)
+      for (int j = n0 + tid; j < n1; j += nth) W.vk[c * np + j] = 0.0;
+    grid_barrier(g);
+    for (int c = 0; c < nc; c++) {
+      const int a = a0 + c;
+      if (a % nb != b) continue;
+      const double sa = W.s[a];
+      for (int k = W.rp[a] + tid; k < W.rp[a + 1]; k += nth) {
+        const int col = W.ci[k];
+        W.vk[c * np + col] = Dinv[col] * W.val[k] * sa;
+      }
+    }
+    grid_barrier(g);
+    for (int r = b; r < w; r += nb) {
+      double acc[kWoodCols];
+#pragma unroll
+      for (int c = 0; c < kWoodCols; c++) acc[c] = 0.0;
+      for (int k = W.rp[r] + tid; k < W.rp[r + 1]; k += nth) {
+        const int col = W.ci[k];
+        const double a = W.val[k];
+#pragma unroll
+        for (int c = 0; c < kWoodCols; c++)
+          if (c < nc) acc[c] = fma(a, W.vk[c * np + col], acc[c]);
+      }
+      const double sr = W.s[r];
+      for (int c = 0; c < nc; c++) {
+        const double sum = block_sum(sm, acc[c]);
+        if (tid == 0) W.C[r * ld + a0 + c] = sr * sum + (r == a0 + c ? 1.0 : 0.0);
+      }
+    }
+    grid_barrier(g);
+  }
+  if (b == 0) wood_factor(W);
+  grid_barrier(g);
+}
+
+// u = M^{-1} r for the Woodbury preconditioner, given v = Dinv .* r in W.v (written by the caller, made visible by a
+// grid barrier).  Returns this thread's share of gamma = r'u; the caller reduces it (its barrier also publishes u).
+__device__ __noinline__ double wood_apply(Grid &g, RedSmem &sm, const DevPtrs &d, const double *Dinv,
+                                          const double *rvec, double *uvec, int n0, int n1) {
+  const WoodDev &W = d.W;
+  const int tid = threadIdx.x, nth = blockDim.x, b = blockIdx.x, nb = gridDim.x;
+  const int lane = tid & 31, warp = tid >> 5, w = W.w, ld = W.ld;
+  // t = S A_W v: one thread block per member row (these rows are long)
+  for (int r = b; r < w; r += nb) {
+    double acc = 0.0;
+    for (int k = W.rp[r] + tid; k < W.rp[r + 1]; k += nth) acc = fma(W.val[k], W.v[W.ci[k]], acc);
+    const double sum = block_sum(sm, acc);
+    if (tid == 0) W.t[r] = W.s[r] * sum;
+  }
+  grid_barrier(g);
+  // g = S Cinv t: one warp per entry, spread over the grid
+  for (int a = b * kWarps + warp; a < w; a += nb * kWarps) {
+    double acc = 0.0;
+    for (int k = lane; k < w; k += 32) acc = fma(W.Cinv[a * ld + k], __ldcg(W.t + k), acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) W.g[a] = W.s[a] * acc;
+  }
+  grid_barrier(g);
+  // u = v - Dinv .* (A_W' g) on the rows this block owns: 16 lanes per row
+  constexpr int kL = 16;
+  const int sub = tid & (kL - 1), grp = tid / kL, ngrp = nth / kL;
+  double gam = 0.0;
+  for (int base = n0; base < n1; base += ngrp) {
+    const int row = base + grp;
+    const bool valid = row < n1;
+    double acc = 0.0;
+    if (valid)
+      for (int k = W.trp[row] + sub; k < W.trp[row + 1]; k += kL) acc = fma(W.tval[k], __ldcg(W.g + W.tci[k]), acc);
+    for (int o = kL >> 1; o; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, kL);
+    if (valid && sub == 0) {
+      const double u = store_u(d, uvec, row, W.v[row] - Dinv[row] * acc);
+      gam += rvec[row] * u;
+    }
+  }
+  return gam;
 }
 
 // Residual refresh on the tile streams: z_tilde = A x_tilde, tr = rho .* z_tilde and
@@ -1079,6 +1289,9 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   }
   grid_barrier(g);
 
+  const bool wood = d.blocked && d.W.w > 0;
+  if (wood && c.wood_refresh) wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+
   InfoScalars S;
   S.pri_res = S.dua_res = S.obj_val = 0.0;
   long long status = ST_UNSOLVED, info_iter = 0, cg_total = 0, cg_solves = 0, checks = 0, log_rows = 0, refreshes = 0;
@@ -1129,8 +1342,9 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
         const double rj = refresh ? bj - d.w[j] : d.r[j] + (bj - d.b[j]);
         d.b[j] = bj;
         d.r[j] = rj;
-        const double uj = d.Minv[j] * rj;
-        d.uu[j] = uj;
+        double uj = d.Minv[j] * rj;
+        if (wood) d.W.v[j] = uj;
+        else uj = store_u(d, d.uu, j, uj);
         red3[0] += rj * uj;
         red3[1] = fmax(red3[1], fabs(rj));
         red3[2] = fmax(red3[2], fabs(bj));
@@ -1162,14 +1376,20 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
         else rj = d.r[row] + (bj - d.b[row]);
         d.b[row] = bj;
         d.r[row] = rj;
-        const double uj = d.Minv[row] * rj;
-        d.uu[row] = uj;
+        double uj = d.Minv[row] * rj;
+        if (wood) d.W.v[row] = uj;
+        else uj = store_u(d, d.uu, row, uj);
         red3[0] += rj * uj;
         red3[1] = fmax(red3[1], fabs(rj));
         red3[2] = fmax(red3[2], fabs(bj));
       }
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
+    if (wood) {
+      double redg[1] = {wood_apply(g, sm, d, d.Minv, d.r, d.uu, n0, n1)};
+      reduce_and_barrier<1>(g, sm, redg, 0u);
+      red3[0] = redg[0];
+    }
     pc.tick(refresh ? 11 : 10);
     refreshes += refresh;
     refresh = 0;
@@ -1276,8 +1496,12 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
           if (ct == 0) { d.rho_vec[i] = rho; d.rho_inv[i] = 1.0 / rho; }
           else if (ct == 1) { d.rho_vec[i] = kRhoEqOverIneq * rho; d.rho_inv[i] = 1.0 / (kRhoEqOverIneq * rho); }
         }
-        grid_barrier(g);
-        precond_rows(d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        if (wood) {
+          wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        } else {
+          grid_barrier(g);
+          precond_rows(d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        }
         pc.tick(13);
         refresh = 1;  // K changed: the residual recurrence is void
       }
@@ -1362,7 +1586,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
 // run CG on (P + sigma I) v = b for a pseudo-random b: CG's pivots p'(P+sigma I)p are the pivots
 // of the Lanczos tridiagonal, so a non-positive one appears as soon as the smallest Ritz value
 // crosses zero (exact after n steps; extreme eigenvalues converge first).
-__global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const __grid_constant__ DevPtrs d, double sigma, int max_it) {
+__global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const __grid_constant__ DevPtrs d, double sigma, int max_it,
+                                                               int trials) {
   __shared__ RedSmem sm;
   Grid g;
   grid_init(g, d);
@@ -1370,56 +1595,77 @@ __global__ void __launch_bounds__(kThreads, 1) pd_probe_kernel(const __grid_cons
   const int n0 = d.n_start[b], n1 = d.n_start[b + 1];
   const int lanesN = d.At.lanes;
   const int subN = tid & (lanesN - 1), grpN = tid / lanesN, ngrpN = nth / lanesN;
-  double red[1] = {0.0};
-  for (int j = n0 + tid; j < n1; j += nth) {
-    unsigned h = (unsigned)j * 2654435761u + 12345u;
-    h ^= h >> 15; h *= 2246822519u; h ^= h >> 13;
-    const double v = ((double)(h & 0xFFFFFF) / 16777216.0) - 0.5 + 1e-3;
-    d.r[j] = v;
-    d.p[j] = v;
-    red[0] += v * v;
-  }
-  reduce_and_barrier<1>(g, sm, red, 0u);
-  double rr = red[0];
-  const double rr0 = rr;
   int failed = 0;
-  for (int it = 0; it < max_it && rr > 1e-26 * rr0; it++) {
-    red[0] = 0.0;
-    for (int base = n0; base < n1; base += ngrpN) {
-      const int row = base + grpN;
-      const bool valid = row < n1;
-      Acc<1> acc;
-      acc.a[0] = 0.0;
-      row_accumulate<1>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
-                        [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * d.p[c]; });
-      group_reduce<1>(acc, lanesN);
-      if (valid && subN == 0) {
-        const double pj = d.p[row];
-        const double wj = acc.a[0] + sigma * pj;
-        d.w[row] = wj;
-        red[0] += wj * pj;
-      }
-    }
-    reduce_and_barrier<1>(g, sm, red, 0u);
-    const double pw = red[0];
-    if (!(pw > 0.0)) {
-      failed = 1;
-      break;
-    }
-    const double a = rr / pw;
-    red[0] = 0.0;
+  // Every trial runs CG from its own pseudo-random right-hand side until the residual has dropped by 1e-10 (the
+  // Krylov space then holds every eigen-direction the start vector excites above that level, and a negative one
+  // would have shown up as a non-positive pivot on the way) or the iteration budget is spent.
+  for (int trial = 0; trial < trials && !failed; trial++) {
+    double red[1] = {0.0};
     for (int j = n0 + tid; j < n1; j += nth) {
-      const double rj = d.r[j] - a * d.w[j];
-      d.r[j] = rj;
-      red[0] += rj * rj;
+      unsigned h = (unsigned)j * 2654435761u + 12345u + 977u * (unsigned)trial;
+      h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+      const double v = ((double)(h & 0xFFFFFF) / 16777216.0) - 0.5 + 1e-3;
+      d.r[j] = v;
+      d.p[j] = v;
+      red[0] += v * v;
     }
     reduce_and_barrier<1>(g, sm, red, 0u);
-    const double beta = red[0] / rr;
-    rr = red[0];
-    for (int j = n0 + tid; j < n1; j += nth) d.p[j] = d.r[j] + beta * d.p[j];
-    grid_barrier(g);
+    double rr = red[0];
+    const double rr0 = rr;
+    for (int it = 0; it < max_it && rr > 1e-20 * rr0; it++) {
+      red[0] = 0.0;
+      for (int base = n0; base < n1; base += ngrpN) {
+        const int row = base + grpN;
+        const bool valid = row < n1;
+        Acc<1> acc;
+        acc.a[0] = 0.0;
+        row_accumulate<1>(d.P.rowptr, d.P.col, d.P.val, row, valid, subN, lanesN, acc,
+                          [&](Acc<1> &ac, int c, double a) { ac.a[0] += a * d.p[c]; });
+        group_reduce<1>(acc, lanesN);
+        if (valid && subN == 0) {
+          const double pj = d.p[row];
+          const double wj = acc.a[0] + sigma * pj;
+          d.w[row] = wj;
+          red[0] += wj * pj;
+        }
+      }
+      reduce_and_barrier<1>(g, sm, red, 0u);
+      const double pw = red[0];
+      if (!(pw > 0.0)) {
+        failed = 1;
+        break;
+      }
+      const double a = rr / pw;
+      red[0] = 0.0;
+      for (int j = n0 + tid; j < n1; j += nth) {
+        const double rj = d.r[j] - a * d.w[j];
+        d.r[j] = rj;
+        red[0] += rj * rj;
+      }
+      reduce_and_barrier<1>(g, sm, red, 0u);
+      const double beta = red[0] / rr;
+      rr = red[0];
+      for (int j = n0 + tid; j < n1; j += nth) d.p[j] = d.r[j] + beta * d.p[j];
+      grid_barrier(g);
+    }
   }
   if (b == 0 && tid == 0) d.state->pd_check_failed = failed;
+}
+
+// Gershgorin certificate on the scaled P + sigma I: strictly diagonally dominant rows with a positive diagonal prove
+// positive definiteness in one pass over P (diagonal, banded-dominant and regularised-Laplacian Hessians all pass).
+// One warp per row; state->pd_certified must be 1 on entry and is cleared by any row that fails.
+__global__ void k_gershgorin(const DevPtrs d, double sigma) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < d.n; r += nwarps) {
+    double off = 0.0;
+    for (int k = d.P.rowptr[r] + lane; k < d.P.rowptr[r + 1]; k += 32)
+      if (d.P.col[k] != r) off += fabs(d.P.val[k]);
+    for (int o = 16; o; o >>= 1) off += __shfl_xor_sync(0xffffffffu, off, o);
+    if (lane == 0 && !(d.Pdiag[r] + sigma > off)) d.state->pd_certified = 0;
+  }
 }
 
 // ------------------------------------------------------------------ polish (row a12)
@@ -1464,8 +1710,10 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
   reduce_and_barrier<1>(g, sm, cnt, 0u);
   const long long n_active = (long long)(cnt[0] + 0.5);
   // preconditioner for K_pol
-  precond_rows(d, d.pol_rho, c.delta, d.pol_rhs /* reused as Minv_pol below */, n0, n1);
-  double *Minv_pol = d.pol_rhs;
+  double *Minv_pol = d.pol_rhs;  // pol_rhs is free here
+  const bool wood = d.blocked && d.W.w > 0;
+  if (wood) wood_refresh(g, sm, d, d.pol_rho, c.delta, Minv_pol, n0, n1);
+  else precond_rows(d, d.pol_rho, c.delta, Minv_pol, n0, n1);
   long long cg_total = 0;
   for (int outer = 0; outer <= c.refine_iter; outer++) {
     // z = A x (fresh), wv = penalty*(b - z) - y on active rows : K dx = -(P x + q + delta*0) + A'(wv) ...
@@ -1503,14 +1751,20 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
       if (valid && subN == 0) {
         const double rj = -d.q[row] - acc.a[1] + acc.a[0];
         d.r[row] = rj;
-        const double uj = Minv_pol[row] * rj;
-        d.uu[row] = uj;
+        double uj = Minv_pol[row] * rj;
+        if (wood) d.W.v[row] = uj;
+        else uj = store_u(d, d.uu, row, uj);
         red3[0] += rj * uj;
         red3[1] = fmax(red3[1], fabs(rj));
         red3[2] = fmax(red3[2], fabs(d.q[row]) + fabs(acc.a[1]));  // scale of the stationarity terms, penalty-free
       }
     }
     reduce_and_barrier<3>(g, sm, red3, 0x6u);
+    if (wood) {
+      double redg[1] = {wood_apply(g, sm, d, Minv_pol, d.r, d.uu, n0, n1)};
+      reduce_and_barrier<1>(g, sm, redg, 0u);
+      red3[0] = redg[0];
+    }
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
     {
       const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
@@ -1988,6 +2242,16 @@ __global__ void k_fill_blocked(const DevPtrs d) {
   for (long long k = tid; k < d.P.nnz; k += nth) d.SA.val[d.SA.from_csr[d.A.nnz + k]] = d.P.val[k];
 }
 
+// compact copies of the Woodbury member rows <- scaled CSR values of A
+__global__ void k_fill_wood(const DevPtrs d) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  const long long nnzW = d.W.w > 0 ? d.W.rp[d.W.w] : 0;
+  for (long long k = tid; k < nnzW; k += nth) {
+    d.W.val[k] = d.A.val[d.W.src[k]];
+    d.W.tval[k] = d.A.val[d.W.tsrc[k]];
+  }
+}
+
 inline int ew_grid(long long work) {
   long long g = (work + 255) / 256;
   if (g < 1) g = 1;
@@ -2059,10 +2323,15 @@ cudaError_t launch_precond(const DevPtrs &d, double sigma, cudaStream_t st) {
   return cudaGetLastError();
 }
 
-cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, cudaStream_t st) {
+cudaError_t launch_pd_probe(const DevPtrs &d, LaunchGeom g, double sigma, int max_it, int trials, cudaStream_t st) {
   g.dyn_smem = 0;
   g.cluster = 1;
-  return coop_launch(pd_probe_kernel, d.bar, g, st, d, sigma, max_it);
+  return coop_launch(pd_probe_kernel, d.bar, g, st, d, sigma, max_it, trials);
+}
+
+cudaError_t launch_gershgorin(const DevPtrs &d, double sigma, cudaStream_t st) {
+  k_gershgorin<<<ew_grid((long long)d.n * 32), 256, 0, st>>>(d, sigma);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_warm_start(const DevPtrs &d, const double *x_in, const double *y_in, int scaling, cudaStream_t st) {
@@ -2181,6 +2450,11 @@ int max_coop_blocks_per_sm(int block, size_t dyn_smem) {
 
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st) {
   if (d.blocked) k_fill_blocked<<<ew_grid(d.A.nnz + d.P.nnz), 256, 0, st>>>(d);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_wood(const DevPtrs &d, cudaStream_t st) {
+  if (d.W.w > 0) k_fill_wood<<<148 * 4, 256, 0, st>>>(d);
   return cudaGetLastError();
 }
 

@@ -73,6 +73,7 @@ struct Engine {
   int pcg_max_iter = 0, refresh_every = 25;
   double polish_penalty = 1e4;
   bool first_run = true, clear_update_time = false;
+  bool wood_dirty = true;  // WoodDev data must be rebuilt by the next launch (setup, re-scaling, rho / bound updates, polish)
   OSQPB200Profile prof;
 };
 
@@ -277,6 +278,15 @@ struct TileStreamHost {
 bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int ngroups, bool paired,
                        TileStreamHost &T, int max_pair_rows = 1 << 30) {
   if (paired && (ngroups != 2 || (grid & 1))) paired = false;
+  const bool dbg = getenv("OSQP_B200_DEBUG") != nullptr;
+  double t_mark = now_s();
+  auto mark = [&](const char *what) {
+    if (dbg) {
+      const double t = now_s();
+      fprintf(stderr, "[osqp_b200]   stream build: %-24s %7.1f ms\n", what, (t - t_mark) * 1e3);
+      t_mark = t;
+    }
+  };
   int rows = 0;
   long long nnz = 0;
   for (const CsrRef &M : mats) { rows += M.rows; nnz += (*M.rowptr)[M.rows]; }
@@ -300,6 +310,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       r0 += M.rows;
     }
   }
+  mark("count per (row, group)");
   // quads of a row inside a group (a row without entries there still costs one zero quad)
   auto quads_of = [](int c) { return std::max(1, (c + 3) >> 2); };
   // Stream rows.  A row with more than `split_quads` quads in a group is cut into pieces of that many quads, each
@@ -340,6 +351,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   }
   if (nnz > 0 && (double)stored > 1.35 * (double)nnz + 4096.0) return false;  // padding would dominate
   if (stored > 2147483000LL) return false;
+  mark("stream rows, weights");
   // thread blocks per group, proportional to the stored quads (every group gets at least one)
   std::vector<int> nblk(ngroups, 1);
   {
@@ -421,6 +433,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   if (getenv("OSQP_B200_DEBUG"))
     fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d split=%d stream rows=%d max_block_rows=%d\n", rows, cols,
             ngroups, T.paired, T.split, T.srows, T.max_block_rows);
+  mark("block / warp ranges");
   // positions: warp by warp, stream row by stream row; every stream row is a whole number of quads and every warp's
   // stream starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
   std::vector<std::vector<int>> sr_start(ngroups);
@@ -440,6 +453,7 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   T.w_q0[(size_t)grid * kWarps] = (int)(pos / 4);
   if (pos > 2147483000LL) return false;
   T.nelem = pos;
+  mark("positions");
   T.cf.assign((size_t)pos + 8, 0);
   T.from_csr.resize(nnz);
   std::vector<int> cursor((size_t)rows * ngroups, 0);  // entries of (row, group) placed so far
@@ -462,9 +476,11 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       k0 += (*M.rowptr)[M.rows];
     }
   }
+  mark("place entries");
   for (int g = 0; g < ngroups; g++)
     for (size_t sr = 0; sr + 1 < wpre[g].size(); sr++)
       T.cf[sr_start[g][sr] + 4 * (wpre[g][sr + 1] - wpre[g][sr]) - 1] |= 0x8000u;
+  mark("row-end flags");
   return true;
 }
 
@@ -549,8 +565,72 @@ c_int rescale_and_refresh(Engine &e, bool reset_rho_types) {
   }
   CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
   CU_OK(launch_fill_blocked(e.d, e.stream));
-  e.prof.launches += 2;
+  CU_OK(launch_fill_wood(e.d, e.stream));
+  e.wood_dirty = true;
+  e.prof.launches += 2 + (e.d.W.w > 0 ? 1 : 0);
   return 0;
+}
+
+// Convexity check of osqp_setup / osqp_update_P (libosqp: the LDL' of the KKT matrix must have n positive pivots, i.e.
+// the scaled P + sigma I must be positive definite; test/non_convex.jl:13-21 needs setup to FAIL otherwise).  Three
+// tiers, cheapest first: (1) Gershgorin certificate on the device, one pass over P; (2) n <= kDenseCholMax: exact --
+// dense Cholesky of the scaled P + sigma I on the host (the verdict of a factorisation, like libosqp's); (3) larger n:
+// CG / Lanczos curvature probe on the device from several start vectors with a residual-based stopping rule and an
+// iteration budget that grows with n.  (3) cannot prove definiteness -- an indefinite direction that none of the
+// start vectors excites above 1e-10 escapes it; PCG breakdown inside the ADMM loop (Non_convex) is the second net.
+constexpr int kDenseCholMax = 640;
+
+c_int convexity_check(Engine &e, int *nonconvex) {
+  DevPtrs &d = e.d;
+  const int n = d.n;
+  *nonconvex = 0;
+  { c_int rc = pull_state(e); if (rc) return rc; }  // the cost scaling c was just written on the device
+  e.h_state->pd_certified = 1;
+  e.h_state->pd_check_failed = 0;
+  { c_int rc = push_state(e); if (rc) return rc; }
+  CU_OK(launch_gershgorin(d, e.st.sigma, e.stream));
+  e.prof.launches += 1;
+  { c_int rc = pull_state(e); if (rc) return rc; }
+  if (e.h_state->pd_certified && !env_int("OSQP_B200_NO_GERSHGORIN", 0)) return 0;
+  if (n <= env_int("OSQP_B200_DENSE_CHOL_MAX", kDenseCholMax)) {
+    const long long nnzP = d.P.nnz;
+    std::vector<int> rp(n + 1), ci(nnzP);
+    std::vector<double> val(nnzP);
+    CU_OK(cudaMemcpyAsync(rp.data(), d.P.rowptr, (size_t)(n + 1) * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+    if (nnzP > 0) {
+      CU_OK(cudaMemcpyAsync(ci.data(), d.P.col, (size_t)nnzP * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+      CU_OK(cudaMemcpyAsync(val.data(), d.P.val, (size_t)nnzP * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    }
+    CU_OK(cudaStreamSynchronize(e.stream));
+    std::vector<double> L((size_t)n * n, 0.0);  // row-major, lower triangle
+    for (int i = 0; i < n; i++) {
+      for (int k = rp[i]; k < rp[i + 1]; k++)
+        if (ci[k] <= i) L[(size_t)i * n + ci[k]] += val[k];
+      L[(size_t)i * n + i] += e.st.sigma;
+    }
+    for (int j = 0; j < n && !*nonconvex; j++) {  // left-looking: the inner loops are contiguous dot products
+      const double *Lj = &L[(size_t)j * n];
+      double dj = Lj[j];
+      for (int k = 0; k < j; k++) dj -= Lj[k] * Lj[k];
+      if (!(dj > 0.0)) { *nonconvex = 1; break; }
+      const double r = std::sqrt(dj), rinv = 1.0 / r;
+      L[(size_t)j * n + j] = r;
+      for (int i = j + 1; i < n; i++) {
+        double *Li = &L[(size_t)i * n];
+        double a = Li[j];
+        for (int k = 0; k < j; k++) a -= Li[k] * Lj[k];
+        Li[j] = a * rinv;
+      }
+    }
+    return 0;
+  }
+  const int budget = env_int("OSQP_B200_PD_PROBE_ITERS", std::min(n, 2000));
+  CU_OK(launch_pd_probe(d, e.geom, e.st.sigma, budget, env_int("OSQP_B200_PD_PROBE_TRIALS", 3), e.stream));
+  e.prof.launches += 1;
+  { c_int rc = pull_state(e); if (rc) return rc; }
+  *nonconvex = e.h_state->pd_check_failed;
+  e.h_state->pd_check_failed = 0;
+  return push_state(e);
 }
 
 void publish(Engine &e) {
@@ -1065,7 +1145,8 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
       int gmin = std::max(1, (cols + slice_cap - 1) / slice_cap);
       return std::max(gmin, env_int("OSQP_B200_GROUPS", 0));
     };
-    const bool want = env_int("OSQP_B200_BLOCKED", 1) != 0 && e.geom.grid >= 8 && (nnzA + nnzP) >= 200000;
+    const bool want = env_int("OSQP_B200_BLOCKED", 1) != 0 && e.geom.grid >= 8 &&
+                      (nnzA + nnzP) >= env_int("OSQP_B200_STREAM_MIN_NNZ", 200000);
     if (want) {
       TileStreamHost hA, hT;
       std::vector<CsrRef> matsA;
@@ -1103,6 +1184,11 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
         { c_int rc = upload_tile_stream(e, hA, d.SA); if (rc) return rc; }
         if (m > 0) { c_int rc = upload_tile_stream(e, hT, d.ST); if (rc) return rc; }
         CU_OK(dalloc(e, &d.Pu, (size_t)n + 8));
+        d.f32_slices = env_int("OSQP_B200_F32_SLICES", 1) != 0;
+        if (d.f32_slices) {
+          CU_OK(dalloc(e, &d.uu32, (size_t)n + 32));
+          CU_OK(dalloc(e, &d.tr32, (size_t)m + 32));
+        }
         CU_OK(configure_dyn_smem(e.geom.dyn_smem));
         if (max_coop_blocks_per_sm(e.geom.block, e.geom.dyn_smem) < 1) {
           fprintf(stderr, "ERROR in osqp_setup: shared-memory slice of %zu bytes does not fit\n", e.geom.dyn_smem);
@@ -1113,6 +1199,52 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
       } else {
         e.geom.dyn_smem = 0;
       }
+    }
+  }
+
+  // ---- low-rank (Woodbury) part of the preconditioner (engine.cuh WoodDev): the few coupling equality rows.
+  // Membership is fixed here from the bounds as passed; it is a choice of preconditioner, not of algorithm -- a row
+  // that later stops (or starts) being an equality only costs PCG iterations.
+  if (d.blocked && m > 0 && env_int("OSQP_B200_WOODBURY", 1) != 0) {
+    std::vector<int> rows;
+    long long nnzW = 0;
+    for (int i = 0; i < m && (int)rows.size() <= kWoodMax; i++)
+      if (data->u[i] - data->l[i] < 1e-4 && A_rowptr[i + 1] - A_rowptr[i] >= 2) {
+        rows.push_back(i);
+        nnzW += A_rowptr[i + 1] - A_rowptr[i];
+      }
+    const int w = (int)rows.size();
+    if (w > 0 && w <= kWoodMax) {
+      WoodDev &W = d.W;
+      std::vector<int> idx(m, -1), rp(w + 1, 0), ci(nnzW), src(nnzW), trp(n + 1, 0), tci(nnzW), tsrc(nnzW);
+      for (int a = 0; a < w; a++) {
+        idx[rows[a]] = a;
+        rp[a + 1] = rp[a] + (A_rowptr[rows[a] + 1] - A_rowptr[rows[a]]);
+        for (int k = A_rowptr[rows[a]], o = rp[a]; k < A_rowptr[rows[a] + 1]; k++, o++) { ci[o] = A_col[k]; src[o] = k; }
+      }
+      {
+        int o = 0;
+        for (int j = 0; j < n; j++) {
+          for (int k = At_rowptr[j]; k < At_rowptr[j + 1]; k++)
+            if (idx[At_col[k]] >= 0) { tci[o] = idx[At_col[k]]; tsrc[o] = mapA[k]; o++; }
+          trp[j + 1] = o;
+        }
+      }
+      W.ld = (w + 7) & ~7;
+#define UPW(dst, vec)                                                                                        \
+  CU_OK(dalloc(e, &dst, (vec).size()));                                                                      \
+  CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
+      UPW(W.rows, rows); UPW(W.idx, idx); UPW(W.rp, rp); UPW(W.ci, ci); UPW(W.src, src);
+      UPW(W.trp, trp); UPW(W.tci, tci); UPW(W.tsrc, tsrc);
+#undef UPW
+      CU_OK(dalloc(e, &W.val, (size_t)nnzW)); CU_OK(dalloc(e, &W.tval, (size_t)nnzW));
+      CU_OK(dalloc(e, &W.C, (size_t)W.ld * W.ld)); CU_OK(dalloc(e, &W.Cinv, (size_t)W.ld * W.ld));
+      CU_OK(dalloc(e, &W.s, (size_t)W.ld)); CU_OK(dalloc(e, &W.t, (size_t)W.ld)); CU_OK(dalloc(e, &W.g, (size_t)W.ld));
+      CU_OK(dalloc(e, &W.v, (size_t)n + 8)); CU_OK(dalloc(e, &W.vk, (size_t)kWoodCols * ((size_t)n + 8)));
+      CU_OK(cudaStreamSynchronize(e.stream));  // the host vectors go out of scope
+      W.w = w;
+      if (env_int("OSQP_B200_DEBUG", 0))
+        fprintf(stderr, "[osqp_b200] Woodbury preconditioner: %d coupling equality rows, %lld non-zeros\n", w, nnzW);
     }
   }
 
@@ -1127,12 +1259,14 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   e.h_state->needs_refresh = 1;
   { c_int rc = push_state(e); if (rc) return rc; }
   { c_int rc = rescale_and_refresh(e, true); if (rc) return rc; }
-  CU_OK(launch_pd_probe(d, e.geom, e.st.sigma, std::min(n, env_int("OSQP_B200_PD_PROBE_ITERS", 200)), e.stream));
-  e.prof.launches += 1;
-  { c_int rc = pull_state(e); if (rc) return rc; }
-  if (e.h_state->pd_check_failed) {
-    fprintf(stderr, "ERROR in osqp_setup: P + sigma*I is not positive definite (the problem seems to be non-convex)\n");
-    return 7;
+  {
+    int nonconvex = 0;
+    c_int rc = convexity_check(e, &nonconvex);
+    if (rc) return rc;
+    if (nonconvex) {
+      fprintf(stderr, "ERROR in osqp_setup: P + sigma*I is not positive definite (the problem seems to be non-convex)\n");
+      return 7;
+    }
   }
 
   mark("scaling, rho, precond, probe");
@@ -1202,6 +1336,7 @@ static c_int solve_impl(Engine &e) {
   c.time_limit_s = e.st.time_limit > 0 ? e.st.time_limit - base : -1e30;
   c.pcg_eta = e.pcg_eta; c.pcg_floor = e.pcg_floor; c.pcg_max_iter = e.pcg_max_iter;
   c.refresh_every = e.refresh_every;
+  c.wood_refresh = (e.d.W.w > 0 && e.wood_dirty) ? 1 : 0;
   if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
   // Automatic adaptive-rho interval (settings.adaptive_rho_interval = 0).  libosqp derives it from wall-clock:
   // the first iteration after 0.4 * setup_time, rounded to a multiple of check_termination -- a trade between the
@@ -1222,6 +1357,7 @@ static c_int solve_impl(Engine &e) {
   CU_OK(launch_with_pair_fallback(e, [&]() { return launch_solve(e.d, c, e.geom, e.stream); }));
   CU_OK(cudaEventRecord(e.ev1, e.stream));
   e.prof.launches += 1;
+  e.wood_dirty = false;  // the launch leaves the Woodbury data consistent with the rho it ends on
   const int n = e.d.n, m = e.d.m;
   CU_OK(cudaMemcpyAsync(e.h_info, e.d.info, sizeof(DevInfo), cudaMemcpyDeviceToHost, e.stream));
   CU_OK(cudaMemcpyAsync(e.h_sol_x, e.d.sol_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
@@ -1289,6 +1425,7 @@ static c_int solve_impl(Engine &e) {
     pc.scaled_termination = c.scaled_termination;
     CU_OK(launch_with_pair_fallback(e, [&]() { return launch_polish(e.d, pc, c, e.d_pol, e.geom, e.stream); }));
     CU_OK(cudaEventRecord(e.ev2, e.stream));
+    e.wood_dirty = true;  // polish rebuilt the Woodbury data for its own penalty vector
     e.prof.launches += 1;
     CU_OK(cudaMemcpyAsync(e.h_pol, e.d_pol, sizeof(PolishOut), cudaMemcpyDeviceToHost, e.stream));
     CU_OK(cudaMemcpyAsync(e.h_sol_x, e.d.sol_x, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, e.stream));
@@ -1346,6 +1483,7 @@ static c_int bounds_changed(Engine &e) {
   CU_OK(launch_scale_vectors(e.d, 0, 1, e.stream));
   CU_OK(launch_set_rho_vec(e.d, e.st.rho, 1, e.stream));
   CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
+  e.wood_dirty = true;
   e.prof.launches += 3;
   CU_OK(cudaStreamSynchronize(e.stream));
   reset_info(e);
@@ -1461,13 +1599,10 @@ static c_int update_PA(Engine &e, const c_float *Px_new, const c_int *Px_idx, c_
   }
   // unscale -> overwrite -> scale of libosqp == re-equilibrate the stored originals
   { c_int rc = rescale_and_refresh(e, false); if (rc) return rc; }
-  CU_OK(launch_pd_probe(e.d, e.geom, e.st.sigma, std::min(e.d.n, env_int("OSQP_B200_PD_PROBE_ITERS", 200)), e.stream));
-  e.prof.launches += 1;
-  { c_int rc = pull_state(e); if (rc) return rc; }
+  int failed = 0;
+  { c_int rc = convexity_check(e, &failed); if (rc) return rc; }
   reset_info(e);
   e.h_state->needs_refresh = 1;
-  const int failed = e.h_state->pd_check_failed;
-  e.h_state->pd_check_failed = 0;
   { c_int rc = push_state(e); if (rc) return rc; }
   e.info.update_time += now_s() - t0;
   if (failed) {
@@ -1558,6 +1693,7 @@ c_int osqp_update_rho(OSQPWorkspace *work, c_float rho_new) {
   { c_int rc = push_state(e); if (rc) return rc; }
   CU_OK(launch_apply_rho(e.d, e.st.rho, e.stream));
   CU_OK(launch_precond(e.d, e.st.sigma, e.stream));
+  e.wood_dirty = true;
   e.prof.launches += 2;
   CU_OK(cudaStreamSynchronize(e.stream));
   e.info.update_time += now_s() - t0;

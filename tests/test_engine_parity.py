@@ -379,3 +379,66 @@ def test_settings_variants_at_stream_size(pkg, engine_lib, oracle_lib, extra):
     tol = 1e-5 if e.info.status == "Solved" else 1e-3
     assert np.max(np.abs(e.x - o.x)) <= 10 * tol * (1 + np.max(np.abs(o.x)))
     assert np.max(np.abs(e.y - o.y)) <= 10 * tol * (1 + np.max(np.abs(o.y)))
+
+
+def _shifted_hessian(n, density, seed, lam_min):
+    """Sparse symmetric P (not diagonally dominant) whose smallest eigenvalue is `lam_min`."""
+    from scipy.sparse.linalg import eigsh
+
+    rng = np.random.default_rng(seed)
+    S = sp.random(n, n, density=density, random_state=rng, data_rvs=rng.standard_normal, format="csc")
+    P0 = (S + S.T).tocsc()
+    lo = float(eigsh(P0, k=1, which="SA", return_eigenvectors=False, tol=1e-10)[0])
+    return (P0 + (lam_min - lo) * sp.identity(n, format="csc")).tocsc()
+
+
+@pytest.mark.parametrize("n,density,tier", [(400, 0.03, "dense Cholesky on the host"), (5000, 0.002, "CG probe on the device")])
+def test_setup_rejects_mildly_indefinite_hessian(pkg, engine_lib, n, density, tier):
+    # test/non_convex.jl:13-21 at sizes where the 2 x 2 example's shortcut (a negative diagonal) does not exist:
+    # smallest eigenvalue -1e-3 => setup must fail; the same matrix shifted to +1e-3 must set up and solve
+    rng = np.random.default_rng(n)
+    A = sp.random(n // 2, n, density=0.01, random_state=rng, data_rvs=rng.standard_normal, format="csc")
+    base = dict(q=rng.standard_normal(n), A=A, l=-np.ones(n // 2), u=np.ones(n // 2))
+    bad = pkg.Model(lib=engine_lib)
+    with pytest.raises(RuntimeError):
+        bad.setup(P=_shifted_hessian(n, density, 3, -1e-3), verbose=False, **base)
+    good = pkg.Model(lib=engine_lib)
+    good.setup(P=_shifted_hessian(n, density, 3, 1e-3), verbose=False, eps_abs=1e-4, eps_rel=1e-4, **base)
+    r = good.solve()
+    assert r.info.status in ("Solved", "Max_iter_reached"), (tier, r.info.status)
+    good.clean()
+
+
+def test_update_P_to_indefinite_is_refused(pkg, engine_lib):
+    # osqp_update_P re-runs the convexity check (src/interface.jl:336-344 raises on a non-zero exit code)
+    n = 300
+    P = _shifted_hessian(n, 0.05, 5, 1e-2)
+    rng = np.random.default_rng(2)
+    A = sp.identity(n, format="csc")
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(P=P, q=rng.standard_normal(n), A=A, l=-np.ones(n), u=np.ones(n), verbose=False)
+    Pt = sp.triu(P, format="csc")
+    Pbad = sp.triu(_shifted_hessian(n, 0.05, 5, -1e-2), format="csc")
+    assert (Pt.indices == Pbad.indices).all() and (Pt.indptr == Pbad.indptr).all()
+    with pytest.raises(RuntimeError):
+        mdl.update(Px=Pbad.data)
+    mdl.clean()
+
+
+def test_two_models_with_different_slices_coexist(pkg, engine_lib):
+    # ADVICE r1: cudaFuncAttributeMaxDynamicSharedMemorySize is per function and process; a second, smaller tile-stream
+    # model must not lower the cap under the first one
+    big = random_qp(40000, 60000, 0.0008, 71)     # two column groups, paired: close to the full shared memory
+    small = random_qp(6000, 9000, 0.006, 72)      # one small slice
+    opts = dict(FIXED_RHO, eps_abs=1e-3, eps_rel=1e-3, check_termination=25)
+    m1 = pkg.Model(lib=engine_lib)
+    m1.setup(**big, **opts)
+    r1 = m1.solve()
+    m2 = pkg.Model(lib=engine_lib)
+    m2.setup(**small, **opts)
+    r2 = m2.solve()
+    r1b = m1.solve()  # would fail with cudaErrorInvalidValue if the attribute had been lowered
+    assert r1.info.status == r2.info.status == r1b.info.status == "Solved"
+    assert r1b.info.iter <= r1.info.iter  # warm-started from the solution
+    m1.clean()
+    m2.clean()
