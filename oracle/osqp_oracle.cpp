@@ -1008,6 +1008,18 @@ c_int osqp_oracle_num_threads(void) {
   return 1;
 #endif
 }
+// `count` independent workspaces solved concurrently, one workspace per task (each solve itself is single-threaded,
+// like libosqp): the CPU arm of bench.py for the batched configuration -- a plain C loop, so that the comparison is
+// not against the interpreter that would otherwise drive the solves one by one
+c_int osqp_solve(OSQPWorkspace *work);
+c_int osqp_oracle_solve_many(OSQPWorkspace **works, c_int count) {
+  c_int bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : bad)
+#endif
+  for (c_int k = 0; k < count; k++) bad += osqp_solve(works[k]) != 0;
+  return bad;
+}
 // y = A x / y = A' x on a caller-provided CSC matrix (SpMV parity checks)
 void osqp_oracle_mat_vec(const csc *A, const c_float *x, c_float *y, c_int transpose) {
   Csc M;

@@ -557,28 +557,34 @@ __device__ __forceinline__ void fast_pat(FastPat &Q, const FastDims &d, const sh
 // row i of A times the n-vector in shared memory `v`
 __device__ __forceinline__ double arow(const FastPat &Q, const double *Av, const double *v, int i, int m) {
   double a = 0.0;
-  if (i < m)
+  if (i < m) {
+#pragma unroll 1
     for (int k = Q.Arp[i]; k < Q.Arp[i + 1]; k++) a = fma(Av[Q.Acq[k]], v[Q.Acc[k]], a);
+  }
   return a;
 }
 // column j of A times the m-vector in shared memory `v`  (= row j of A')
 __device__ __forceinline__ double acol(const FastPat &Q, const double *Av, const double *v, int j, int n) {
   double a = 0.0;
-  if (j < n)
+  if (j < n) {
+#pragma unroll 1
     for (int k = Q.Acp[j]; k < Q.Acp[j + 1]; k++) a = fma(Av[k], v[Q.Ari[k]], a);
+  }
   return a;
 }
 __device__ __forceinline__ double prow(const FastPat &Q, const double *Pv, const double *v, int j, int n) {
   double a = 0.0;
-  if (j < n)
+  if (j < n) {
+#pragma unroll 1
     for (int k = Q.Prp[j]; k < Q.Prp[j + 1]; k++) a = fma(Pv[Q.Pcq[k]], v[Q.Pcc[k]], a);
+  }
   return a;
 }
 
 // K = P + sigma I + A' diag(rho) A into W.L (row-major, lower triangle used), then Cholesky; lane j builds column j
 // of K on its own (no conflicts, fixed order).  rho of rows lane / lane + 32 in r0 / r1.  Returns false on a
 // non-positive pivot (uniform over the warp).
-__device__ bool fast_factor(const FastWarp &W, const FastPat &Q, const FastDims &d, double sigma, double r0, double r1) {
+__device__ __noinline__ bool fast_factor(const FastWarp &W, const FastPat &Q, const FastDims &d, double sigma, double r0, double r1) {
   const int n = d.n, m = d.m, lane = threadIdx.x & 31;
   if (lane < m) W.vm0[lane] = r0;
   if (lane + 32 < m) W.vm0[lane + 32] = r1;
@@ -869,11 +875,18 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
     __syncwarp();
   };
 
-  long long it = 0, info_iter = 0;
+  // Iteration counters are 32-bit countdowns (a 64-bit `it % check_termination` is a software division in the hot
+  // loop), and update_info has ONE call site: the last iteration is checked inside the loop like any other, so the
+  // (large) body of info() is instantiated once -- the loop body must stay small enough for the instruction cache
+  // with 16 warps per SM at unrelated points of it.
+  const int max_iter = (int)(c.max_iter < 2000000000LL ? c.max_iter : 2000000000LL);
+  const int chk = (int)(c.check_termination < 2000000000LL ? c.check_termination : 2000000000LL);
+  const int adp = (c.adaptive_rho && adaptive_interval > 0)
+                      ? (int)(adaptive_interval < 2000000000LL ? adaptive_interval : 2000000000LL) : 0;
+  int it = 0, info_iter = 0, to_check = chk, to_adapt = adp;
   double rho_est = rho;
-  bool checked = false;
   if (status == ST_UNSOLVED)
-    for (it = 1; it <= c.max_iter; it++) {
+    for (it = 1; it <= max_iter; it++) {
       // rhs = sigma x - q + A'(rho z - y)
       if (h0) W.vm0[lane] = r0 * z0 - y0;
       if (h1) W.vm0[i1] = r1 * z1 - y1;
@@ -904,15 +917,17 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
         else if (l1 < -kInfty * kMinScaling) dd = fmax(dd, 0.0);
         dy1 = dd;
       }
-      checked = c.check_termination && (it % c.check_termination == 0);
-      const bool adapt = c.adaptive_rho && adaptive_interval && (it % adaptive_interval == 0);
-      if (checked || adapt) {
-        info();
-        info_iter = it;
-        if (checked) {
-          status = check_termination(I, c, m, cost_c, cost_cinv, false);
-          if (status != ST_UNSOLVED) break;
-        }
+      const bool checked = chk > 0 && --to_check == 0;
+      const bool adapt = adp > 0 && --to_adapt == 0;
+      const bool last = it == max_iter;
+      if (!(checked || adapt || last)) continue;
+      if (checked) to_check = chk;
+      if (adapt) to_adapt = adp;
+      info();
+      info_iter = it;
+      if (checked || last) {  // libosqp checks the last iterate after the loop if the loop did not (Appendix A)
+        status = check_termination(I, c, m, cost_c, cost_cinv, false);
+        if (status != ST_UNSOLVED) break;
       }
       if (adapt) {
         const double rho_new = rho_estimate(I, rho);
@@ -926,18 +941,12 @@ __global__ void __launch_bounds__(32 * kFastWarps, 4) batch_fast_solve_kernel(
           refactor = true;
         }
       }
+      if (last) {  // not solved after max_iter iterations: the x10 tolerances decide between *_inaccurate and Max_iter
+        const long long s2 = check_termination(I, c, m, cost_c, cost_cinv, true);
+        status = (s2 != ST_UNSOLVED) ? s2 : ST_MAX_ITER;
+        break;
+      }
     }
-  if (status == ST_UNSOLVED) {
-    if (!checked) {
-      info();
-      info_iter = it - 1;
-      status = check_termination(I, c, m, cost_c, cost_cinv, false);
-    }
-    if (status == ST_UNSOLVED) {
-      const long long s2 = check_termination(I, c, m, cost_c, cost_cinv, true);
-      status = (s2 != ST_UNSOLVED) ? s2 : ST_MAX_ITER;
-    }
-  }
   if (status != ST_NON_CVX) rho_est = rho_estimate(I, rho);
   double obj_val = I.obj_val;
   if (status == ST_NON_CVX) obj_val = nan("");

@@ -46,7 +46,10 @@ struct CsrDev {
 //   * A lane sums its quad; row sums are formed with a warp-segmented scan over the per-lane flags (carry across
 //     chunks) and written straight to part[group][row].  The owner blocks add the `ngroups` partial vectors in the
 //     element-wise phase that follows the next grid barrier (fixed order -> run-to-run deterministic).
-constexpr int kWarps = 16;          // warps per thread block of the cooperative kernels (kThreads / 32)
+#ifndef OSQP_B200_WARPS
+#define OSQP_B200_WARPS 16
+#endif
+constexpr int kWarps = OSQP_B200_WARPS;  // warps per thread block of the cooperative kernels (kThreads / 32)
 constexpr int kSliceMax = 27648;    // doubles per staged slice (216 KB); local columns are 15-bit
 constexpr int kSplitQuads = 64;     // smallest piece a long row is cut into (build_tile_stream: stream rows)
 
@@ -240,6 +243,8 @@ cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
                         cudaStream_t st);
 int max_coop_blocks_per_sm(int block, size_t dyn_smem);
+int coop_threads();          // threads per block the cooperative kernels are compiled for (kernels.cu kThreads)
+size_t coop_static_smem();   // static shared memory of admm_kernel / polish_kernel (the larger)
 cudaError_t configure_dyn_smem(size_t dyn_smem);
 cudaError_t raise_dyn_smem(const void *func, size_t bytes);  // never lowers the per-device attribute
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st);

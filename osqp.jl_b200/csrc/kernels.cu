@@ -25,7 +25,7 @@ namespace osqpb200 {
 
 namespace {
 
-constexpr int kThreads = 512;  // threads per block of the cooperative kernels: 128 registers per thread
+constexpr int kThreads = 32 * kWarps;  // threads per block of the cooperative kernels (512: 128 registers per thread)
 
 
 // ------------------------------------------------------------------ memory helpers
@@ -150,7 +150,14 @@ __device__ __forceinline__ void l2_prefetch(const void *ptr, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a0), "r"((unsigned)(a1 - a0)) : "memory");
 }
 
-constexpr int kDepth = 4;  // chunks (one quad per lane, 40 B) of matrix stream in flight per lane
+#ifndef OSQP_B200_DEPTH
+#define OSQP_B200_DEPTH 4
+#endif
+#ifndef OSQP_B200_ILP
+#define OSQP_B200_ILP 2
+#endif
+constexpr int kILP = OSQP_B200_ILP;      // chunks whose segmented scans are interleaved (stream_phase_impl consume2)
+constexpr int kDepth = OSQP_B200_DEPTH;  // chunks (one quad per lane, 40 B) of matrix stream in flight per lane
 
 struct QuadSlot {
   double v0, v1, v2, v3;
@@ -278,6 +285,56 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
     rdone += __popc(bal);
   };
 
+  // Two chunks at a time: their gathers and the five steps of their segmented scans are independent until the carry
+  // is handed from the first to the second, which doubles the instruction-level parallelism of the scan -- with 16
+  // warps per SM the phase is bound by the dependent shuffle / add chain of the scan, not by memory
+  // (profiles/r2_ncu_admm.md).
+  auto gather = [&](const QuadSlot &q) {
+    double x0, x1, x2, x3;
+    if (kF32) {
+      x0 = (double)lds_f32(xs + ((q.c01 & 0x7fffu) << 2)); x1 = (double)lds_f32(xs + ((q.c01 >> 14) & 0x1fffcu));
+      x2 = (double)lds_f32(xs + ((q.c23 & 0x7fffu) << 2)); x3 = (double)lds_f32(xs + ((q.c23 >> 14) & 0x1fffcu));
+    } else {
+      x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)); x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+      x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)); x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    }
+    double inc = q.v0 * x0;
+    inc = fma(q.v1, x1, inc);
+    inc = fma(q.v2, x2, inc);
+    return fma(q.v3, x3, inc);
+  };
+  auto consume2 = [&](const QuadSlot &qa, const QuadSlot &qb) {
+    double ia = gather(qa), ib = gather(qb);
+    const bool fa = (qa.c23 >> 31) != 0u, fb = (qb.c23 >> 31) != 0u;
+    const unsigned bala = __ballot_sync(0xffffffffu, fa), balb = __ballot_sync(0xffffffffu, fb);
+    const unsigned bela = bala & lt, belb = balb & lt;
+    const int ha = 32 - __clz(bela), hb = 32 - __clz(belb);
+#pragma unroll
+    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+      const double ta = __shfl_up_sync(0xffffffffu, ia, dlt), tb = __shfl_up_sync(0xffffffffu, ib, dlt);
+      if (lane - dlt >= ha) ia += ta;
+      if (lane - dlt >= hb) ib += tb;
+    }
+    if (bela == 0u) ia += carry;
+    const int ra = rdone + __popc(bela);
+    if (fa) {
+      if (kPair) sts_f64(out_s + 8u * (unsigned)ra, ia);
+      else out[ra] = ia;
+    }
+    const double lasta = __shfl_sync(0xffffffffu, ia, 31);
+    const double ca = (bala >> 31) ? 0.0 : lasta;
+    rdone += __popc(bala);
+    if (belb == 0u) ib += ca;
+    const int rb = rdone + __popc(belb);
+    if (fb) {
+      if (kPair) sts_f64(out_s + 8u * (unsigned)rb, ib);
+      else out[rb] = ib;
+    }
+    const double lastb = __shfl_sync(0xffffffffu, ib, 31);
+    carry = (balb >> 31) ? 0.0 : lastb;
+    rdone += __popc(balb);
+  };
+
   QuadSlot slot[kD];
 #pragma unroll
   for (int k = 0; k < kD; k++) issue(slot[k]);
@@ -285,10 +342,19 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
   if (S.probe != nullptr && tid == 0) S.probe[6] = globaltimer_ns();
   const int nchunks = (L + 31) >> 5;
   for (int base = 0; base < nchunks; base += kD) {
+    if (kILP == 2 && (kD % 2) == 0) {
 #pragma unroll
-    for (int k = 0; k < kD; k++) {
-      consume(slot[k]);  // slots past the end hold zeros without flags: a no-op that keeps carry and rdone
-      issue(slot[k]);
+      for (int k = 0; k < kD; k += 2) {
+        consume2(slot[k], slot[k + 1]);  // slots past the end hold zeros without flags: a no-op
+        issue(slot[k]);
+        issue(slot[k + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < kD; k++) {
+        consume(slot[k]);  // slots past the end hold zeros without flags: a no-op that keeps carry and rdone
+        issue(slot[k]);
+      }
     }
   }
 }
@@ -2438,6 +2504,17 @@ cudaError_t configure_dyn_smem(size_t dyn_smem) {
   e = raise_dyn_smem((const void *)spmv_stream_kernel, dyn_smem);
   if (e != cudaSuccess) return e;
   return raise_dyn_smem((const void *)polish_kernel, dyn_smem);
+}
+
+int coop_threads() { return kThreads; }
+
+size_t coop_static_smem() {
+  cudaFuncAttributes a{}, b{};
+  if (cudaFuncGetAttributes(&a, admm_kernel) != cudaSuccess || cudaFuncGetAttributes(&b, polish_kernel) != cudaSuccess) {
+    cudaGetLastError();
+    return 16384;
+  }
+  return a.sharedSizeBytes > b.sharedSizeBytes ? a.sharedSizeBytes : b.sharedSizeBytes;
 }
 
 int max_coop_blocks_per_sm(int block, size_t dyn_smem) {

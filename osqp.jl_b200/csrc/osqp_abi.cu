@@ -1062,7 +1062,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   // ---- launch geometry
   cudaDeviceProp prop;
   CU_OK(cudaGetDeviceProperties(&prop, e.device));
-  e.geom.block = std::min(512, env_int("OSQP_B200_BLOCK", 512));  // kernels.cu kThreads
+  e.geom.block = std::min(coop_threads(), env_int("OSQP_B200_BLOCK", coop_threads()));
   const int per_sm = max_coop_blocks_per_sm(e.geom.block, 0);
   if (per_sm <= 0) {
     fprintf(stderr, "ERROR in osqp_setup: the sm_100a kernels cannot run on device %d (%s, sm_%d%d)\n", e.device,
@@ -1138,7 +1138,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   // ---- tile streams for the hot phases (engine.cuh TileStreamDev)
   {
     d.blocked = 0;
-    const long long smem_budget = (long long)prop.sharedMemPerBlockOptin - 4352 /* static RedSmem */ - 640;
+    const long long smem_budget = (long long)prop.sharedMemPerBlockOptin - (long long)coop_static_smem() - 384;
     const int slice_cap = std::min<long long>(std::min(kSliceMax, env_int("OSQP_B200_SLICE", kSliceMax)),
                                               (smem_budget - 128) / 8);
     auto groups_for = [&](int cols) {

@@ -25,12 +25,13 @@ ap.add_argument("--density", type=float, default=bench.DENSITY)
 ap.add_argument("--solves", type=int, default=1)
 ap.add_argument("--max-iter", type=int, default=4000)
 ap.add_argument("--spmv-reps", type=int, default=2)
+ap.add_argument("--lib", default=graft.LIB, help="engine library (a compile-time variant from profiles/variants.py)")
 args = ap.parse_args()
 
 pkg = graft.load_package()
-eng = pkg.load_library(graft.LIB)
+eng = pkg.load_library(args.lib)
 prob = bench.make_problem(args.n, args.m, args.density, bench.SEED)
-mdl = pkg.Model(lib=graft.LIB)
+mdl = pkg.Model(lib=args.lib)
 mdl.setup(**prob, **dict(bench.SETTINGS, max_iter=args.max_iter, warm_start=False))
 PHASES = ["stream[A;P]", "barrier", "combine", "reduce+bar", "stream A'", "barrier", "vectors", "reduce+bar",
           "admm z/y/x+bar", "admm A'rhs+bar", "admm rhs+red", "refresh", "update_info", "rho upd", "epilogue", "-"]

@@ -99,3 +99,25 @@ def test_cleanup_accepts_null(pkg, oracle_lib):
     m.clean()
     with pytest.raises(RuntimeError):
         m.solve()  # test/interface.jl:15-18
+
+
+def test_jll_override_directory(pkg, engine_lib):
+    # override/ is the artefact a Julia user copies; Julia cannot run here, so check what can be:
+    # the uuid is OSQP_jll's (reference Project.toml:13), the preference key names the JLL's library product, the
+    # symlink resolves to the engine, and the engine answers the version string smoke.jl looks for
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ov = os.path.join(root, "override")
+    uuid = "9c4f68bf-6205-5545-a508-2878b064d984"
+    ref = "/root/reference/Project.toml"
+    if os.path.exists(ref):
+        assert f'OSQP_jll = "{uuid}"' in open(ref).read()
+    assert f"[{uuid}]" in open(os.path.join(ov, "artifacts", "Overrides.toml")).read()
+    prefs = open(os.path.join(ov, "LocalPreferences.toml")).read()
+    assert "[OSQP_jll]" in prefs and "osqp_path" in prefs and "lib/libosqp.so" in prefs
+    link = os.path.join(ov, "prefix", "lib", "libosqp.so")
+    assert os.path.islink(link) and os.path.realpath(link) == os.path.realpath(engine_lib)
+    lib = C.CDLL(link)
+    lib.osqp_version.restype = C.c_char_p
+    assert b"b200" in lib.osqp_version()
+    for sym in pkg.ABI_SYMBOLS:
+        assert hasattr(lib, sym)
