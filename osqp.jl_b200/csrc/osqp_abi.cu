@@ -73,6 +73,14 @@ struct Engine {
   int pcg_max_iter = 0, refresh_every = 25;
   double polish_penalty = 1e4;
   bool first_run = true, clear_update_time = false;
+  // ---- tiny mode (n, m <= kTinyMax): the same QP also lives in the batched engine (batch.cu, a batch of one: dense /
+  // sparse KKT in shared memory, exact Cholesky solve, ~1 us per ADMM iteration instead of the ~60 us of a
+  // grid-synchronised PCG step on a problem with a handful of non-zeros).  osqp_solve uses it whenever the solve needs
+  // nothing the batched engine lacks (polish, time limit, verbose log); every update is applied to both engines.
+  OSQPB200Batch *tiny = nullptr;
+  std::vector<c_int> tP_p, tP_i, tA_p, tA_i;  // host copies of the problem as passed (re-setup after P / A / rho updates)
+  std::vector<double> tP_x, tA_x, tq;
+  int last_path = 0;  // 0: none yet, 1: general engine, 2: tiny engine -- iterates are handed over on a switch
   bool wood_dirty = true;  // WoodDev data must be rebuilt by the next launch (setup, re-scaling, rho / bound updates, polish)
   OSQPB200Profile prof;
 };
@@ -120,6 +128,8 @@ cudaError_t halloc(Engine &e, T **p, size_t count) {
 void destroy(Engine *e) {
   if (!e) return;
   DeviceGuard guard(e->device);
+  if (e->tiny) osqp_batch_cleanup(e->tiny);
+  e->tiny = nullptr;
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (void *p : e->dev_allocs) cudaFree(p);
   for (void *p : e->host_allocs) cudaFreeHost(p);
@@ -681,6 +691,111 @@ double spmv_bytes(long long nnz, long long rows, long long cols) {
 
 c_int upload_vector(Engine &e, double *dst, const c_float *src, long long count) {
   if (count > 0) CU_OK(cudaMemcpyAsync(dst, src, count * sizeof(double), cudaMemcpyHostToDevice, e.stream));
+  return 0;
+}
+
+constexpr int kTinyMax = 256;
+
+// (Re-)create the tiny engine from the host copies of the problem; `rho` is the rho to start from.  Iterates are not
+// carried over by this call (the caller warm-starts from the last solution when there is one).
+c_int tiny_setup(Engine &e, double rho) {
+  if (e.tiny) { osqp_batch_cleanup(e.tiny); e.tiny = nullptr; }
+  const c_int n = e.d.n, m = e.d.m;
+  csc Pc{}, Ac{};
+  Pc.nzmax = (c_int)e.tP_x.size(); Pc.m = n; Pc.n = n; Pc.p = e.tP_p.data(); Pc.i = e.tP_i.data(); Pc.x = e.tP_x.data(); Pc.nz = -1;
+  Ac.nzmax = (c_int)e.tA_x.size(); Ac.m = m; Ac.n = n; Ac.p = e.tA_p.data(); Ac.i = e.tA_i.data(); Ac.x = e.tA_x.data(); Ac.nz = -1;
+  OSQPData pat{};
+  pat.n = n; pat.m = m; pat.P = &Pc; pat.A = &Ac;
+  OSQPSettings st = e.st;
+  st.rho = rho;
+  st.verbose = 0;
+  st.polish = 0;
+  const c_int rc = osqp_batch_setup(&e.tiny, 1, &pat, e.tP_x.data(), e.tA_x.data(), e.tq.data(), e.l0.data(), e.u0.data(), &st);
+  if (rc != 0) e.tiny = nullptr;  // the general engine still serves the workspace
+  return 0;
+}
+
+bool use_tiny(const Engine &e) {
+  return e.tiny != nullptr && !e.st.polish && e.st.time_limit == 0 && !e.st.verbose;
+}
+
+bool has_solution(c_int sv) {
+  return sv == OSQP_SOLVED || sv == OSQP_SOLVED_INACCURATE || sv == OSQP_MAX_ITER_REACHED;
+}
+
+c_int tiny_solve(Engine &e) {
+  if (e.clear_update_time) e.info.update_time = 0.0;
+  const double t0 = now_s();
+  const int n = e.d.n, m = e.d.m;
+  OSQPB200Batch *b = e.tiny;
+  const OSQPSettings &s = e.st;
+  osqp_batch_update_setting(b, "max_iter", (double)s.max_iter);
+  osqp_batch_update_setting(b, "eps_abs", s.eps_abs);
+  osqp_batch_update_setting(b, "eps_rel", s.eps_rel);
+  osqp_batch_update_setting(b, "eps_prim_inf", s.eps_prim_inf);
+  osqp_batch_update_setting(b, "eps_dual_inf", s.eps_dual_inf);
+  osqp_batch_update_setting(b, "alpha", s.alpha);
+  osqp_batch_update_setting(b, "check_termination", (double)s.check_termination);
+  osqp_batch_update_setting(b, "warm_start", (double)s.warm_start);
+  osqp_batch_update_setting(b, "scaled_termination", (double)s.scaled_termination);
+  if (s.adaptive_rho && s.adaptive_rho_interval == 0) {  // the same deterministic rule as solve_impl
+    const long long N = s.check_termination > 0 ? s.check_termination : 25;
+    long long iv = ((50 + N / 2) / N) * N;
+    if (iv < N) iv = N;
+    e.st.adaptive_rho_interval = iv;
+  }
+  osqp_batch_update_setting(b, "adaptive_rho_interval", (double)s.adaptive_rho_interval);
+  if (e.last_path == 1 && s.warm_start && has_solution(e.info.status_val))  // the general engine solved last: hand over
+    osqp_batch_warm_start(b, e.h_sol_x, m > 0 ? e.h_sol_y : nullptr);
+  const c_float *x = nullptr, *y = nullptr;
+  const OSQPB200BatchInfo *bi = nullptr;
+  const c_int rc = osqp_batch_solve_view(b, &x, &y, &bi);
+  if (rc != 0) return rc;
+  const c_int sv = bi->status_val;
+  e.info.iter = bi->iter;
+  update_status(e.info, sv);
+  e.info.status_polish = 0;
+  e.info.obj_val = bi->obj_val;
+  e.info.pri_res = bi->pri_res;
+  e.info.dua_res = bi->dua_res;
+  e.info.rho_updates = bi->rho_updates;
+  e.info.rho_estimate = bi->rho_estimate;
+  const bool pinf = sv == OSQP_PRIMAL_INFEASIBLE || sv == OSQP_PRIMAL_INFEASIBLE_INACCURATE;
+  const bool dinf = sv == OSQP_DUAL_INFEASIBLE || sv == OSQP_DUAL_INFEASIBLE_INACCURATE;
+  if (pinf || dinf) {  // the batched engine returns the certificate in place of the solution
+    if (pinf) memcpy(e.h_dy, y, (size_t)m * sizeof(double));
+    if (dinf) memcpy(e.h_dx, x, (size_t)n * sizeof(double));
+    for (int j = 0; j < n; j++) e.h_sol_x[j] = NAN;
+    for (int i = 0; i < m; i++) e.h_sol_y[i] = NAN;
+  } else {
+    memcpy(e.h_sol_x, x, (size_t)n * sizeof(double));
+    if (m > 0) memcpy(e.h_sol_y, y, (size_t)m * sizeof(double));
+  }
+  e.prof.kernel_ms = osqp_batch_last_kernel_ms(b);
+  e.prof.polish_ms = 0;
+  e.prof.admm_iters = bi->iter;
+  e.prof.pcg_iters = 0;
+  e.prof.launches += 1;
+  e.last_path = 2;
+  const double base = e.first_run ? e.info.setup_time : e.info.update_time;
+  e.info.solve_time = now_s() - t0;
+  e.info.polish_time = 0;
+  e.info.run_time = base + e.info.solve_time;
+  e.first_run = false;
+  e.clear_update_time = true;
+  e.pub.first_run = 0;
+  return 0;
+}
+
+// After a change that the batched engine cannot take in place (P / A values, rho): rebuild it and restart it from the
+// last solution, as libosqp keeps its iterates across osqp_update_P / osqp_update_rho.
+c_int tiny_rebuild(Engine &e) {
+  if (!e.tiny) return 0;
+  const bool carry = e.last_path == 2 && has_solution(e.info.status_val);
+  std::vector<double> x, y;
+  if (carry) { x.assign(e.h_sol_x, e.h_sol_x + e.d.n); y.assign(e.h_sol_y, e.h_sol_y + e.d.m); }
+  tiny_setup(e, e.st.rho);
+  if (e.tiny && carry) osqp_batch_warm_start(e.tiny, x.data(), e.d.m > 0 ? y.data() : nullptr);
   return 0;
 }
 
@@ -1288,6 +1403,13 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   e.prof.groups_A = d.blocked ? d.SA.ngroups : 0;
   e.prof.groups_At = (d.blocked && m > 0) ? d.ST.ngroups : 0;
   e.prof.paired = d.blocked ? d.SA.paired : 0;
+  // ---- tiny mode: the same QP in the batched engine (a batch of one)
+  if (n <= kTinyMax && m <= kTinyMax && env_int("OSQP_B200_TINY", 1) != 0) {
+    e.tP_p.assign(Pc->p, Pc->p + n + 1); e.tP_i.assign(Pc->i, Pc->i + nnzPt); e.tP_x.assign(Pc->x, Pc->x + nnzPt);
+    e.tA_p.assign(Ac->p, Ac->p + n + 1); e.tA_i.assign(Ac->i, Ac->i + nnzA); e.tA_x.assign(Ac->x, Ac->x + nnzA);
+    e.tq.assign(data->q, data->q + n);
+    tiny_setup(e, e.st.rho);
+  }
   publish(e);
   e.info.setup_time = now_s() - t0;
   if (e.st.verbose) print_setup_header(e);
@@ -1297,6 +1419,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
 }
 
 static c_int solve_impl(Engine &e);
+static c_int warm(Engine &e, const c_float *x, const c_float *y);
 
 // The reference ignores osqp_solve's return value (src/interface.jl:170-175) and reads info / solution straight from
 // the workspace.  libosqp cannot fail between a successful setup and the end of a solve; a GPU engine can (launch
@@ -1306,7 +1429,15 @@ c_int osqp_solve(OSQPWorkspace *work) {
   if (!work) { fprintf(stderr, "ERROR in osqp_solve: workspace not initialized\n"); return 1; }
   Engine &e = *E(work);
   DeviceGuard guard(e.device);
-  const c_int rc = solve_impl(e);
+  c_int rc;
+  if (use_tiny(e)) {
+    rc = tiny_solve(e);
+  } else {
+    if (e.last_path == 2 && e.st.warm_start && has_solution(e.info.status_val))  // the tiny engine solved last: hand over
+      warm(e, e.h_sol_x, e.d.m > 0 ? e.h_sol_y : nullptr);
+    rc = solve_impl(e);
+    e.last_path = 1;
+  }
   if (rc != 0) {
     update_status(e.info, OSQP_UNSOLVED);
     e.info.iter = 0;
@@ -1348,6 +1479,7 @@ static c_int solve_impl(Engine &e) {
     const long long N = e.st.check_termination > 0 ? e.st.check_termination : 25;
     long long iv = ((50 + N / 2) / N) * N;
     if (iv < N) iv = N;
+    if (e.st.adaptive_rho_interval > 0) iv = e.st.adaptive_rho_interval;  // already fixed by a tiny-mode solve
     e.h_state->adaptive_interval = iv;
     e.st.adaptive_rho_interval = iv;
     { c_int rc = push_state(e); if (rc) return rc; }
@@ -1475,6 +1607,10 @@ c_int osqp_update_lin_cost(OSQPWorkspace *work, const c_float *q_new) {
   CU_OK(cudaStreamSynchronize(e.stream));  // q_new is caller-owned
   reset_info(e);
   { c_int rc = push_state(e); if (rc) return rc; }
+  if (e.tiny) {
+    e.tq.assign(q_new, q_new + e.d.n);
+    osqp_batch_update(e.tiny, q_new, nullptr, nullptr);
+  }
   e.info.update_time += now_s() - t0;
   return 0;
 }
@@ -1488,6 +1624,7 @@ static c_int bounds_changed(Engine &e) {
   CU_OK(cudaStreamSynchronize(e.stream));
   reset_info(e);
   e.h_state->needs_refresh = 1;
+  if (e.tiny) osqp_batch_update(e.tiny, nullptr, e.l0.data(), e.u0.data());
   return push_state(e);
 }
 
@@ -1604,6 +1741,12 @@ static c_int update_PA(Engine &e, const c_float *Px_new, const c_int *Px_idx, c_
   reset_info(e);
   e.h_state->needs_refresh = 1;
   { c_int rc = push_state(e); if (rc) return rc; }
+  if (e.tiny) {  // same values into the host copies the tiny engine is rebuilt from
+    if (doP) for (long long t = 0, k = Px_idx ? P_n : e.nnzPtriu; t < k; t++) e.tP_x[Px_idx ? Px_idx[t] : t] = Px_new[t];
+    if (doA) for (long long t = 0, k = Ax_idx ? A_n : e.nnzA; t < k; t++) e.tA_x[Ax_idx ? Ax_idx[t] : t] = Ax_new[t];
+    if (failed) { osqp_batch_cleanup(e.tiny); e.tiny = nullptr; }
+    else tiny_rebuild(e);
+  }
   e.info.update_time += now_s() - t0;
   if (failed) {
     fprintf(stderr, "ERROR in osqp_update_P/A: new KKT matrix is not quasidefinite\n");
@@ -1637,17 +1780,26 @@ static c_int warm(Engine &e, const c_float *x, const c_float *y) {
   CU_OK(cudaStreamSynchronize(e.stream));
   return 0;
 }
+// both engines of a tiny-mode workspace take the caller's start; neither owes the other a hand-over afterwards
+static c_int warm_both(Engine &e, const c_float *x, const c_float *y) {
+  const c_int rc = warm(e, x, y);
+  if (rc == 0 && e.tiny) {
+    osqp_batch_warm_start(e.tiny, x, e.d.m > 0 ? y : nullptr);
+    e.last_path = 0;
+  }
+  return rc;
+}
 c_int osqp_warm_start(OSQPWorkspace *work, const c_float *x, const c_float *y) {
   if (!work) return 1;
-  return warm(*E(work), x, y);
+  return warm_both(*E(work), x, y);
 }
 c_int osqp_warm_start_x(OSQPWorkspace *work, const c_float *x) {
   if (!work) return 1;
-  return warm(*E(work), x, nullptr);
+  return warm_both(*E(work), x, nullptr);
 }
 c_int osqp_warm_start_y(OSQPWorkspace *work, const c_float *y) {
   if (!work) return 1;
-  return warm(*E(work), nullptr, y);
+  return warm_both(*E(work), nullptr, y);
 }
 
 // ---- settings (a15)
@@ -1696,6 +1848,7 @@ c_int osqp_update_rho(OSQPWorkspace *work, c_float rho_new) {
   e.wood_dirty = true;
   e.prof.launches += 2;
   CU_OK(cudaStreamSynchronize(e.stream));
+  tiny_rebuild(e);
   e.info.update_time += now_s() - t0;
   return 0;
 }

@@ -1,6 +1,7 @@
 mkdir -p gpurun_out
-for v in w16d4i1 w16d4i2 w32d2i1 w32d2i2 w32d4i2; do echo "== variant $v"; (timeout 120 python profiles/profile_driver.py --solves 2 --lib osqp.jl_b200/lib/variants/libosqp_$v.so 2>&1 | grep -v "^spmv" | tail -3); done
+(timeout 1500 python -m pytest tests -m gpu -q -x --durations=6 --deselect tests/test_bench_parity.py::test_c2_bench_instance > gpurun_out/pytest_gpu.log 2>&1); tail -25 gpurun_out/pytest_gpu.log
 (timeout 100 python profiles/batch_bench.py 2>&1 | tail -3)
-(timeout 300 python -m pytest tests/test_batch.py tests/test_bench_parity.py::test_c5_bench_batch_subset -m gpu -q -x 2>&1 | tail -3)
-for B in 64 128 512; do echo "block $B"; (OSQP_B200_BLOCK=$B timeout 120 python profiles/latency_small.py 2>&1 | tail -7); done
-(timeout 600 ncu --set full --import-source on --clock-control none -k regex:admm_kernel -c 1 -o gpurun_out/admm_prof python profiles/profile_driver.py --solves 1 --max-iter 30 --spmv-reps 1 --lib osqp.jl_b200/lib/variants/libosqp_w16d4i1.so 2>&1 | tail -3)
+(timeout 120 python profiles/latency_small.py 2>&1 | tail -7)
+(OSQP_B200_TINY=0 timeout 120 python profiles/latency_small.py 2>&1 | tail -7)
+(OSQP_B200_DEBUG=1 timeout 300 python bench.py --steps 3 --no-cpu-baseline --no-extras > gpurun_out/bench_dbg.json 2> gpurun_out/bench_dbg.err); grep "osqp_b200\] setup" gpurun_out/bench_dbg.err | head; python -c "
+import json; d=json.load(open('gpurun_out/bench_dbg.json')); print(d['value'], d['solve']['setup_s'], d['roofline']['frac'])"
