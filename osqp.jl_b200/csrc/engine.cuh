@@ -70,6 +70,15 @@ struct TileStreamDev {
   int *w_row0 = nullptr;         // [grid * kWarps] first stacked row of warp i
   int *w_q0 = nullptr;           // [grid * kWarps + 1] first quad of warp i's stream (a multiple of 32 = one chunk)
   int *w_qn = nullptr;           // [grid * kWarps] quads in warp i's stream
+  // Lane-row layout (lane_rows == 1, the default): the stream rows of a block are sorted by length and dealt 32 at a
+  // time into SLICES; lane l of a slice owns stream row sl_row[slice * 32 + l] (-1: none) and finds quad t of it in
+  // chunk t of the slice, so a row sum is a private accumulator of the lane (no segmented scan, no row-end flags).
+  // A slice is sl_len[slice] chunks long (its longest row; shorter rows are zero-padded); warp i streams slices
+  // [w_s0[i], w_s0[i + 1]) back to back from quad w_q0[i].  lane_rows == 0: the scan layout described above.
+  int lane_rows = 0;
+  int *w_s0 = nullptr;           // [grid * kWarps + 1]
+  int *sl_len = nullptr;         // [slices]
+  int *sl_row = nullptr;         // [slices * 32] stream-row index inside the group
   int split = 0;                 // 1: some rows are cut into several stream rows (engine.cuh kSplitQuads)
   int srows = 0;                 // stream rows per group (stride of `part`); == rows when nothing is split
   int *sr_ptr = nullptr;         // [ngroups][rows + 1] first stream row of each row (identity when split == 0)

@@ -359,11 +359,119 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
   }
 }
 
+// The same phase on the lane-row layout (TileStreamDev::lane_rows): lane l of a slice owns one stream row and meets
+// quad t of it in chunk t of the slice, so the row sum is a private accumulator -- per chunk three loads, four gathers
+// and four fused multiply-adds per lane, no ballot, no shuffles, no carry between chunks.  The slice descriptors
+// (length, row of this lane) of the NEXT slice are loaded while the current one streams.
+#ifndef OSQP_B200_DEPTH_LR
+#define OSQP_B200_DEPTH_LR 4
+#endif
+constexpr int kDepthLR = OSQP_B200_DEPTH_LR;
+
+template <int kD, bool kPair, bool kF32>
+__device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, const void *__restrict__ vec) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
+  const int grp = __ldg(T.blk_group + b);
+  const unsigned parity = S.parity;
+  S.parity ^= 1u;
+  if (tid == 0) {
+    asm volatile("fence.proxy.async;" ::: "memory");
+    const int col0 = __ldg(T.grp_col0 + grp), ncols = __ldg(T.grp_col0 + grp + 1) - col0;
+    const unsigned bytes = ((unsigned)ncols * (kF32 ? 4u : 8u) + 15u) & ~15u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(S.mbar), "r"(bytes) : "memory");
+    const char *g = reinterpret_cast<const char *>(vec) + (size_t)col0 * (kF32 ? 4u : 8u);
+    for (unsigned off = 0; off < bytes; off += 32768u) {
+      const unsigned chunk = (bytes - off < 32768u) ? (bytes - off) : 32768u;
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       S.xs + off),
+                   "l"(g + off), "r"(chunk), "r"(S.mbar)
+                   : "memory");
+    }
+  }
+  const int wid = b * kWarps + warp;
+  const int q0 = __ldg(T.w_q0 + wid), nchunks = __ldg(T.w_qn + wid) >> 5;  // whole chunks only
+  if (nchunks <= 0) {
+    if (warp == 0) mbar_wait(S.mbar, parity);  // keep the mbarrier phases in step
+    return;
+  }
+  double *__restrict__ out = T.part + (size_t)grp * T.srows;
+  const unsigned out_s = kPair ? S.ys - 8u * (unsigned)__ldg(T.blk_row0 + b) : 0u;
+  int sl = __ldg(T.w_s0 + wid);
+  const int sl_end = __ldg(T.w_s0 + wid + 1);
+  int left = __ldg(T.sl_len + sl), myrow = __ldg(T.sl_row + (size_t)sl * 32 + lane);
+  int nleft = 0, nrow = -1;
+  if (sl + 1 < sl_end) { nleft = __ldg(T.sl_len + sl + 1); nrow = __ldg(T.sl_row + (size_t)(sl + 1) * 32 + lane); }
+  const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * q0 + 16 * lane;
+  const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
+  const char *pf_v = reinterpret_cast<const char *>(T.val) + 32ll * q0;
+  const char *pf_c = reinterpret_cast<const char *>(T.cf) + 8ll * q0;
+  const int pf = T.pf_chunks;
+  const unsigned xs = S.xs;
+  int issued = 0;
+  double acc = 0.0;
+
+  auto issue = [&](QuadSlot &q) {
+    quad_load(q, pv, pc, issued < nchunks);
+    pv += 1024;
+    pc += 256;
+    if ((issued & 3) == 0 && lane == 0 && pf > 0) {  // every 4th chunk: the 4 chunks `pf` ahead go to L2
+      const int pq = issued + pf;
+      if (pq < nchunks) {
+        const unsigned ch = (unsigned)min(4, nchunks - pq);
+        l2_prefetch(pf_v + 1024ll * pq, ch * 1024u);
+        l2_prefetch(pf_c + 256ll * pq, ch * 256u);
+      }
+    }
+    issued++;
+  };
+  auto consume = [&](const QuadSlot &q) {
+    double x0, x1, x2, x3;
+    if (kF32) {
+      x0 = (double)lds_f32(xs + ((q.c01 & 0x7fffu) << 2)); x1 = (double)lds_f32(xs + ((q.c01 >> 14) & 0x1fffcu));
+      x2 = (double)lds_f32(xs + ((q.c23 & 0x7fffu) << 2)); x3 = (double)lds_f32(xs + ((q.c23 >> 14) & 0x1fffcu));
+    } else {
+      x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)); x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
+      x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)); x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
+    }
+    double inc = q.v0 * x0;
+    inc = fma(q.v1, x1, inc);
+    inc = fma(q.v2, x2, inc);
+    inc = fma(q.v3, x3, inc);
+    acc += inc;
+    if (--left == 0) {  // warp-uniform: the slice ends with this chunk
+      if (myrow >= 0) {
+        if (kPair) sts_f64(out_s + 8u * (unsigned)myrow, acc);
+        else out[myrow] = acc;
+      }
+      acc = 0.0;
+      sl++;
+      left = nleft;
+      myrow = nrow;
+      if (sl + 1 < sl_end) { nleft = __ldg(T.sl_len + sl + 1); nrow = __ldg(T.sl_row + (size_t)(sl + 1) * 32 + lane); }
+    }
+  };
+
+  QuadSlot slot[kD];
+#pragma unroll
+  for (int k = 0; k < kD; k++) issue(slot[k]);
+  mbar_wait(S.mbar, parity);  // the slice has landed (the first matrix loads are already in flight)
+  if (S.probe != nullptr && tid == 0) S.probe[6] = globaltimer_ns();
+  for (int base = 0; base < nchunks; base += kD) {
+#pragma unroll
+    for (int k = 0; k < kD; k++) {
+      if (base + k < nchunks) consume(slot[k]);
+      issue(slot[k]);
+    }
+  }
+}
+
 __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
-  stream_phase_impl<kDepth, false, false>(S, T, vec);
+  if (T.lane_rows) stream_phase_lr<kDepthLR, false, false>(S, T, vec);
+  else stream_phase_impl<kDepth, false, false>(S, T, vec);
 }
 __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &T, const float *__restrict__ vec) {
-  stream_phase_impl<kDepth, false, true>(S, T, vec);
+  if (T.lane_rows) stream_phase_lr<kDepthLR, false, true>(S, T, vec);
+  else stream_phase_impl<kDepth, false, true>(S, T, vec);
 }
 
 // Paired stream (TileStreamDev::paired): blocks 2p / 2p+1 of a cluster stream column groups 0 / 1 of the same row
@@ -374,7 +482,8 @@ __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &
 template <bool kF32 = false, typename Fin>
 __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const void *__restrict__ vec,
                                                     Fin fin) {
-  stream_phase_impl<kDepth, true, kF32>(S, T, vec);
+  if (T.lane_rows) stream_phase_lr<kDepthLR, true, kF32>(S, T, vec);
+  else stream_phase_impl<kDepth, true, kF32>(S, T, vec);
   cluster_sync();
   const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
   const unsigned rank = (unsigned)b & 1u;

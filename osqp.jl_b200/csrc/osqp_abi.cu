@@ -280,14 +280,16 @@ struct TileStreamHost {
   long long nelem = 0, nnz = 0;
   std::vector<unsigned short> cf;
   std::vector<int> from_csr, blk_group, blk_row0, blk_row1, grp_col0, w_row0, w_q0, w_qn, sr_ptr;
-  int max_slice = 0, max_block_rows = 0, paired = 0, split = 0, srows = 0;
+  std::vector<int> w_s0, sl_len, sl_row;  // lane-row layout (engine.cuh TileStreamDev): slices of every warp
+  int max_slice = 0, max_block_rows = 0, paired = 0, split = 0, srows = 0, lane_rows = 0;
 };
 
 // false: the stream does not pay off for this matrix (too much padding) -> CSR path
 // paired: thread-block clusters of two (DSMEM combine of the two column-group partials); needs ngroups == 2.
 bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int ngroups, bool paired,
-                       TileStreamHost &T, int max_pair_rows = 1 << 30) {
+                       TileStreamHost &T, int max_pair_rows = 1 << 30, bool lane_rows = true) {
   if (paired && (ngroups != 2 || (grid & 1))) paired = false;
+  T.sl_len.clear(); T.sl_row.clear(); T.w_s0.clear();
   const bool dbg = getenv("OSQP_B200_DEBUG") != nullptr;
   double t_mark = now_s();
   auto mark = [&](const char *what) {
@@ -332,7 +334,19 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   T.srows = rows;
   long long all_quads = 0;
   for (size_t i = 0; i < cnt.size(); i++) all_quads += quads_of(cnt[i]);
-  const int split_quads = (int)std::max<long long>(kSplitQuads, all_quads / ((long long)grid * kWarps) / 4);
+  // lane rows: a slice (32 stream rows) is as long as its longest row and goes to ONE warp, so pieces must be short
+  // enough that every warp gets several slices: at most 1/128 of a warp's mean load (at least 16 quads).  A row that
+  // would fall into more than 32 such pieces (a few very dense rows next to many short ones: portfolio) makes the
+  // owners' sums over the pieces the bottleneck instead -- measured 13 % slower than the scan layout on config 4 --
+  // so such matrices keep the scan layout.
+  if (lane_rows) {
+    const long long sq = std::max<long long>(16, all_quads / ((long long)grid * kWarps) / 128);
+    int maxq = 0;
+    for (size_t i = 0; i < cnt.size(); i++) maxq = std::max(maxq, quads_of(cnt[i]));
+    if ((long long)maxq > 32 * sq) lane_rows = false;
+  }
+  const int split_quads = lane_rows ? (int)std::max<long long>(16, all_quads / ((long long)grid * kWarps) / 128)
+                                    : (int)std::max<long long>(kSplitQuads, all_quads / ((long long)grid * kWarps) / 4);
   for (int g = 0; g < ngroups; g++) {
     int *sp = T.sr_ptr.data() + (size_t)g * (rows + 1);
     for (int r = 0; r < rows; r++) sp[r + 1] = sp[r] + (quads_of(cnt[(size_t)r * ngroups + g]) + split_quads - 1) / split_quads;
@@ -386,7 +400,6 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
   T.blk_row1.assign(grid, 0);
   T.w_row0.assign((size_t)grid * kWarps, 0);
   T.w_q0.assign((size_t)grid * kWarps + 1, 0);
-  std::vector<int> w_row1((size_t)grid * kWarps, 0);
   // contiguous split of (stream) rows [ra, rb) into `parts` ranges balanced on a weight prefix (every range that
   // still has rows gets at least one)
   auto split = [&](const long long *wp, int ra, int rb, int parts, std::vector<int> &cut, int max_rows = 1 << 30) {
@@ -431,39 +444,99 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
     }
   }
   T.max_block_rows = 0;
-  for (int b = 0; b < grid; b++) {
-    const int g = T.blk_group[b];
-    T.max_block_rows = std::max(T.max_block_rows, T.blk_row1[b] - T.blk_row0[b]);
-    split(wpre[g].data(), T.blk_row0[b], T.blk_row1[b], kWarps, cut);
-    for (int w = 0; w < kWarps; w++) {
-      T.w_row0[(size_t)b * kWarps + w] = cut[w];
-      w_row1[(size_t)b * kWarps + w] = cut[w + 1];
-    }
-  }
+  for (int b = 0; b < grid; b++) T.max_block_rows = std::max(T.max_block_rows, T.blk_row1[b] - T.blk_row0[b]);
+  T.lane_rows = lane_rows ? 1 : 0;
   if (getenv("OSQP_B200_DEBUG"))
-    fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d split=%d stream rows=%d max_block_rows=%d\n", rows, cols,
-            ngroups, T.paired, T.split, T.srows, T.max_block_rows);
-  mark("block / warp ranges");
-  // positions: warp by warp, stream row by stream row; every stream row is a whole number of quads and every warp's
-  // stream starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
-  std::vector<std::vector<int>> sr_start(ngroups);
-  for (int g = 0; g < ngroups; g++) sr_start[g].assign(wpre[g].size(), 0);
+    fprintf(stderr, "[osqp_b200] stream %dx%d groups=%d paired=%d split=%d stream rows=%d max_block_rows=%d lane_rows=%d\n",
+            rows, cols, ngroups, T.paired, T.split, T.srows, T.max_block_rows, T.lane_rows);
+  // first quad of every stream row and the stride between its quads (in quads)
+  std::vector<std::vector<int>> sr_q0(ngroups);
+  for (int g = 0; g < ngroups; g++) sr_q0[g].assign(wpre[g].size(), 0);
+  int qstride = 1;
   T.w_qn.assign((size_t)grid * kWarps, 0);
-  long long pos = 0;
-  for (int wid = 0; wid < grid * kWarps; wid++) {
-    const int g = T.blk_group[wid / kWarps];
-    T.w_q0[wid] = (int)(pos / 4);
-    for (int sr = T.w_row0[wid]; sr < w_row1[wid]; sr++) {
-      sr_start[g][sr] = (int)pos;
-      pos += 4 * (wpre[g][sr + 1] - wpre[g][sr]);
+  long long pos = 0;  // in entries (4 per quad)
+  if (lane_rows) {
+    // Lane-row layout.  The stream rows of a block are sorted by length (quads, descending; ties by index) and dealt
+    // 32 at a time into slices: lane l of a slice owns one stream row and walks its quads one per chunk, so a row sum
+    // is a private accumulator -- no segmented scan, no shuffles.  A slice is as long as its longest row (the sort
+    // keeps the rows of a slice within a quad of each other; shorter rows are padded with zero quads).  Slices go to
+    // the warps of the block longest-first onto the least loaded warp; a warp's slices are stored back to back.
+    qstride = 32;
+    T.w_s0.assign((size_t)grid * kWarps + 1, 0);
+    std::vector<int> order, load(kWarps);
+    std::vector<std::vector<int>> mine(kWarps);
+    for (int b = 0; b < grid; b++) {
+      const int g = T.blk_group[b], ra = T.blk_row0[b], rb = T.blk_row1[b];
+      const long long *wp = wpre[g].data();
+      order.resize(rb - ra);
+      for (int i = 0; i < rb - ra; i++) order[i] = ra + i;
+      std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return wp[x + 1] - wp[x] > wp[y + 1] - wp[y]; });
+      const int nsl = (rb - ra + 31) / 32;
+      std::fill(load.begin(), load.end(), 0);
+      for (auto &v : mine) v.clear();
+      for (int k = 0; k < nsl; k++) {  // slices come out longest first
+        int w = 0;
+        for (int j = 1; j < kWarps; j++) if (load[j] < load[w]) w = j;
+        mine[w].push_back(k);
+        load[w] += (int)(wp[order[(size_t)k * 32] + 1] - wp[order[(size_t)k * 32]]);
+      }
+      for (int w = 0; w < kWarps; w++) {
+        const size_t wid = (size_t)b * kWarps + w;
+        T.w_q0[wid] = (int)(pos / 4);
+        T.w_s0[wid] = (int)T.sl_len.size();
+        for (int k : mine[w]) {
+          const int first = k * 32, cnt = std::min(32, rb - ra - first);
+          const int L = (int)(wp[order[first] + 1] - wp[order[first]]);
+          T.sl_len.push_back(L);
+          for (int l = 0; l < 32; l++) {
+            if (l < cnt) {
+              const int sr = order[first + l];
+              T.sl_row.push_back(sr);
+              sr_q0[g][sr] = (int)(pos / 4) + l;
+            } else {
+              T.sl_row.push_back(-1);
+            }
+          }
+          pos += 128LL * L;
+        }
+        T.w_qn[wid] = (int)(pos / 4) - T.w_q0[wid];
+      }
     }
-    T.w_qn[wid] = (int)(pos / 4) - T.w_q0[wid];
-    pos = (pos + 127) & ~127LL;
+    T.w_s0[(size_t)grid * kWarps] = (int)T.sl_len.size();
+    // Few stream rows per block (or wildly different lengths inside a slice) leave lanes idle: past 25 % more stored
+    // entries than the scan layout needs, use the scan layout
+    if ((double)pos > 1.25 * (double)stored) {
+      T.sl_len.clear(); T.sl_row.clear(); T.w_s0.clear();
+      return build_tile_stream(mats, cols, grid, ngroups, paired, T, max_pair_rows, false);
+    }
+  } else {
+    // scan layout: every warp streams a contiguous range of stream rows, quad by quad across its lanes
+    std::vector<int> w_row1((size_t)grid * kWarps, 0);
+    for (int b = 0; b < grid; b++) {
+      const int g = T.blk_group[b];
+      split(wpre[g].data(), T.blk_row0[b], T.blk_row1[b], kWarps, cut);
+      for (int w = 0; w < kWarps; w++) {
+        T.w_row0[(size_t)b * kWarps + w] = cut[w];
+        w_row1[(size_t)b * kWarps + w] = cut[w + 1];
+      }
+    }
+    // positions: warp by warp, stream row by stream row; every stream row is a whole number of quads and every warp's
+    // stream starts on a chunk (32 quads) so that the value loads of a chunk are two fully coalesced 512 B rows
+    for (int wid = 0; wid < grid * kWarps; wid++) {
+      const int g = T.blk_group[wid / kWarps];
+      T.w_q0[wid] = (int)(pos / 4);
+      for (int sr = T.w_row0[wid]; sr < w_row1[wid]; sr++) {
+        sr_q0[g][sr] = (int)(pos / 4);
+        pos += 4 * (wpre[g][sr + 1] - wpre[g][sr]);
+      }
+      T.w_qn[wid] = (int)(pos / 4) - T.w_q0[wid];
+      pos = (pos + 127) & ~127LL;
+    }
   }
   T.w_q0[(size_t)grid * kWarps] = (int)(pos / 4);
   if (pos > 2147483000LL) return false;
   T.nelem = pos;
-  mark("positions");
+  mark("block / warp ranges, positions");
   T.cf.assign((size_t)pos + 8, 0);
   T.from_csr.resize(nnz);
   std::vector<int> cursor((size_t)rows * ngroups, 0);  // entries of (row, group) placed so far
@@ -477,7 +550,8 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
             const int c = (*M.col)[k], g = c / Wg;
             const int e = cursor[(size_t)(r0 + r) * ngroups + g]++;
             const int piece = (e >> 2) / split_quads;
-            const int p = sr_start[g][T.sr_ptr[(size_t)g * (rows + 1) + r0 + r] + piece] + (e - 4 * split_quads * piece);
+            const int el = e - 4 * split_quads * piece;  // entry inside its stream row
+            const int p = 4 * (sr_q0[g][T.sr_ptr[(size_t)g * (rows + 1) + r0 + r] + piece] + (el >> 2) * qstride) + (el & 3);
             T.cf[p] = (unsigned short)(c - g * Wg);
             T.from_csr[k0 + k] = stream_val_pos(p);
           }
@@ -487,10 +561,12 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
     }
   }
   mark("place entries");
-  for (int g = 0; g < ngroups; g++)
-    for (size_t sr = 0; sr + 1 < wpre[g].size(); sr++)
-      T.cf[sr_start[g][sr] + 4 * (wpre[g][sr + 1] - wpre[g][sr]) - 1] |= 0x8000u;
-  mark("row-end flags");
+  if (!lane_rows) {
+    for (int g = 0; g < ngroups; g++)
+      for (size_t sr = 0; sr + 1 < wpre[g].size(); sr++)
+        T.cf[4 * sr_q0[g][sr] + 4 * (wpre[g][sr + 1] - wpre[g][sr]) - 1] |= 0x8000u;
+    mark("row-end flags");
+  }
   return true;
 }
 
@@ -507,6 +583,8 @@ c_int upload_tile_stream(Engine &e, const TileStreamHost &h, TileStreamDev &t) {
   CU_OK(cudaMemcpyAsync(dst, (vec).data(), (vec).size() * sizeof((vec)[0]), cudaMemcpyHostToDevice, e.stream))
   UP(t.blk_group, h.blk_group); UP(t.grp_col0, h.grp_col0); UP(t.w_row0, h.w_row0); UP(t.w_q0, h.w_q0);
   UP(t.w_qn, h.w_qn); UP(t.blk_row0, h.blk_row0); UP(t.blk_row1, h.blk_row1); UP(t.sr_ptr, h.sr_ptr);
+  t.lane_rows = h.lane_rows;
+  if (h.lane_rows) { UP(t.w_s0, h.w_s0); UP(t.sl_len, h.sl_len); UP(t.sl_row, h.sl_row); }
   t.paired = h.paired;
 #undef UP
   CU_OK(cudaMemcpyAsync(t.cf, h.cf.data(), (size_t)h.nelem * sizeof(unsigned short), cudaMemcpyHostToDevice, e.stream));
@@ -835,7 +913,8 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
   for (c_int k = 0; k < rowptr[rows]; k++) ci[k] = (int)col[k];
   TileStreamHost T;
   std::vector<CsrRef> mats{CsrRef{&rp, &ci, (int)rows}};
-  if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, paired != 0, T)) return 2;
+  if (!build_tile_stream(mats, (int)cols, (int)grid, (int)ngroups, paired != 0, T, 1 << 30, env_int("OSQP_B200_LANE_ROWS", 1) != 0))
+    return 2;
   if (paired && !T.paired) return 2;
   if (T.paired)  // both blocks of a cluster pair must cover the same rows
     for (int b = 0; b < (int)grid; b += 2)
@@ -851,7 +930,41 @@ c_int osqp_b200_stream_selftest(c_int rows, c_int cols, const c_int *rowptr, con
   for (long long k = 0; k < T.nnz; k++) sv[T.from_csr[k]] = val[k];
   std::vector<double> part((size_t)T.ngroups * T.srows, 0.0);
   std::vector<char> written((size_t)T.ngroups * T.srows, 0);
-  for (int wid = 0; wid < (int)grid * kWarps; wid++) {
+  for (int wid = 0; wid < (int)grid * kWarps && T.lane_rows; wid++) {
+    // lane-row layout: replay of kernels.cu stream_phase_lr -- every lane accumulates its own stream row over the
+    // chunks of a slice and stores it when the slice ends
+    const int grp = T.blk_group[wid / kWarps];
+    const int q0 = T.w_q0[wid], L = T.w_qn[wid];
+    if (q0 % 32 != 0 || L % 32 != 0) return 3;
+    const double *xs = x + T.grp_col0[grp];
+    const int slice = T.grp_col0[grp + 1] - T.grp_col0[grp];
+    int chunk = 0;
+    for (int sl = T.w_s0[wid]; sl < T.w_s0[wid + 1]; sl++) {
+      for (int lane = 0; lane < 32; lane++) {
+        double acc = 0.0;
+        for (int t = 0; t < T.sl_len[sl]; t++) {
+          const long long e = 4ll * (q0 + 32 * (chunk + t) + lane);
+          double inc = 0.0;
+          for (int k = 0; k < 4; k++) {
+            const unsigned w = T.cf[e + k];
+            if (w & 0x8000u) return 4;  // no flags in this layout
+            const double v = sv[stream_val_pos((int)(e + k))];
+            if (v != 0.0 && (int)w >= slice) return 5;
+            inc = (k == 0) ? v * xs[w] : std::fma(v, xs[w], inc);
+          }
+          acc += inc;
+        }
+        const int sr = T.sl_row[(size_t)sl * 32 + lane];
+        if (sr < 0) { if (acc != 0.0) return 8; continue; }
+        if (sr < T.blk_row0[wid / kWarps] || sr >= T.blk_row1[wid / kWarps]) return 11;
+        part[(size_t)grp * T.srows + sr] = acc;
+        written[(size_t)grp * T.srows + sr]++;
+      }
+      chunk += T.sl_len[sl];
+    }
+    if (32 * chunk != L) return 6;
+  }
+  for (int wid = 0; wid < (int)grid * kWarps && !T.lane_rows; wid++) {
     const int grp = T.blk_group[wid / kWarps];
     const int q0 = T.w_q0[wid], L = T.w_qn[wid];
     if (L <= 0) continue;
@@ -1282,8 +1395,9 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
         const int Wg = (((n + 1) / 2) + 31) & ~31;
         const long long room = (smem_budget - 64 - 8LL * (((Wg + 2 + 15) & ~15))) / 8 - 16;
         if (paired && room < 64) continue;
-        ok = build_tile_stream(matsA, n, e.geom.grid, groups_for(n), paired, hA, (int)std::min<long long>(room, 1 << 30));
-        if (ok && m > 0 && hT.nelem == 0) ok = build_tile_stream(matsT, m, e.geom.grid, groups_for(m), false, hT);
+        const bool lane_rows = env_int("OSQP_B200_LANE_ROWS", 1) != 0;
+        ok = build_tile_stream(matsA, n, e.geom.grid, groups_for(n), paired, hA, (int)std::min<long long>(room, 1 << 30), lane_rows);
+        if (ok && m > 0 && hT.nelem == 0) ok = build_tile_stream(matsT, m, e.geom.grid, groups_for(m), false, hT, 1 << 30, lane_rows);
         if (!ok) break;
         const int slice = std::max(hA.max_slice, m > 0 ? hT.max_slice : 0);
         d.smem_x_elems = (slice + 2 + 15) & ~15;

@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
-(timeout 1500 python -m pytest tests -m gpu -q -x --durations=6 --deselect tests/test_bench_parity.py::test_c2_bench_instance > gpurun_out/pytest_gpu.log 2>&1); tail -25 gpurun_out/pytest_gpu.log
-(timeout 100 python profiles/batch_bench.py 2>&1 | tail -3)
-(timeout 120 python profiles/latency_small.py 2>&1 | tail -7)
-(OSQP_B200_TINY=0 timeout 120 python profiles/latency_small.py 2>&1 | tail -7)
-(OSQP_B200_DEBUG=1 timeout 300 python bench.py --steps 3 --no-cpu-baseline --no-extras > gpurun_out/bench_dbg.json 2> gpurun_out/bench_dbg.err); grep "osqp_b200\] setup" gpurun_out/bench_dbg.err | head; python -c "
-import json; d=json.load(open('gpurun_out/bench_dbg.json')); print(d['value'], d['solve']['setup_s'], d['roofline']['frac'])"
+for LR in 1 0; do echo "== C3 (5000x25000) lane_rows $LR"; (OSQP_B200_LANE_ROWS=$LR timeout 400 python bench.py --config 3 --lasso 5000x25000x0.15 --steps 1 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['pcg_iters_per_admm_iter'], d['roofline']['frac'], d['solve'])"); done
+for LR in 1 0; do echo "== C4 lane_rows $LR"; (OSQP_B200_LANE_ROWS=$LR timeout 400 python bench.py --config 4 --steps 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline']['pcg_iters_per_admm_iter'], d['solve'])"); done
+(timeout 300 python -m pytest tests/test_configs.py tests/test_engine_parity.py -m gpu -q -x 2>&1 | tail -3)

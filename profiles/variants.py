@@ -14,6 +14,9 @@ VARIANTS = {
     "w32d2i1": dict(OSQP_B200_WARPS=32, OSQP_B200_DEPTH=2, OSQP_B200_ILP=1),
     "w32d2i2": dict(OSQP_B200_WARPS=32, OSQP_B200_DEPTH=2, OSQP_B200_ILP=2),
     "w32d4i2": dict(OSQP_B200_WARPS=32, OSQP_B200_DEPTH=4, OSQP_B200_ILP=2),
+    "lr6": dict(OSQP_B200_DEPTH_LR=6),
+    "lr8": dict(OSQP_B200_DEPTH_LR=8),
+    "lr2": dict(OSQP_B200_DEPTH_LR=2),
 }
 
 if __name__ == "__main__":

@@ -124,3 +124,20 @@ def test_builder_is_independent_of_host_thread_count(pkg, engine_lib, monkeypatc
         assert rc == 0
         ys.append(y)
     assert np.array_equal(ys[0], ys[1]) and np.array_equal(ys[0], ys[2])
+
+
+@pytest.mark.parametrize("lane_rows", ["1", "0"])
+def test_both_layouts_at_bench_like_shape(pkg, engine_lib, monkeypatch, lane_rows):
+    # the lane-row layout (one stream row per lane, sliced-ELL order; the default wherever its padding stays small) and
+    # the scan layout (quads dealt across the lanes, segmented scan) must give the same product
+    monkeypatch.setenv("OSQP_B200_LANE_ROWS", lane_rows)
+    lib = pkg.load_library(engine_lib)
+    rng = np.random.default_rng(5)
+    M = sp.random(30000, 20000, density=0.0025, random_state=rng, data_rvs=rng.standard_normal, format="csr")
+    x = rng.standard_normal(20000)
+    for ngroups, paired in ((1, 0), (2, 0), (2, 1), (4, 0)):
+        rc, y, pad = _run(lib, M, x, 148, ngroups, paired)
+        assert rc == 0
+        scale = np.abs(M) @ np.abs(x) + 1e-300
+        assert np.max(np.abs(y - M @ x) / scale) < 1e-14
+        assert pad < 1.35
