@@ -111,6 +111,23 @@ struct WoodDev {
   double *vk = nullptr;      // [kWoodCols][n + 8] scratch of wood_refresh
 };
 
+// Slack elimination in the preconditioner.  An equality row i whose column j(i) appears in no other row of A and only
+// on the diagonal of P (y in "A_d x - y = b": Lasso, regression, soft constraints) puts K_yy = P_jj + sigma + rho_i a_ij^2
+// on the diagonal of K and couples y_j to the rest only through row i.  The block factorisation
+//   K = [I  K_xy K_yy^-1; 0  I] diag(S, K_yy) [I 0; K_yy^-1 K_yx  I],   S = K_xx - K_xy K_yy^-1 K_yx
+// has a Schur complement S that is K_xx with the equality weight of those rows REDUCED to
+// rho_i (P_jj + sigma) / K_yy (about 2 instead of 100 for the Lasso): Jacobi on S works where Jacobi on K needs one
+// iteration per outlier eigenvalue.  M^-1 r = block back-substitution with diag(S)^-1 in place of S^-1; it costs one
+// extra A' stream phase per PCG iteration (the A phase it needs doubles as the A phase of the next K-apply).
+// Used when there are too many such rows for the dense Woodbury correction (kernels.cu pcg_run_stream_slack).
+struct SlackDev {
+  int rows = 0;            // equality rows with a private slack column (0: off)
+  int *col = nullptr;      // [m] slack column of row i, -1 if none
+  int *pos = nullptr;      // [m] position of a_ij in A.val (CSR)
+  double *rho_eff = nullptr;  // [m] rho with the reduced weight on the slack rows
+  float *g32 = nullptr;    // [m] gather vector of the extra A' phase (zero outside the slack rows)
+};
+
 // Persistent solver state that survives between launches (device memory).
 struct DevState {
   double rho;              // current scalar rho (settings->rho)
@@ -178,6 +195,7 @@ struct DevPtrs {
   int f32_slices = 0;
   float *uu32 = nullptr, *tr32 = nullptr;  // n, m
   WoodDev W;                     // low-rank part of the preconditioner (w == 0: none)
+  SlackDev SL;                   // slack elimination in the preconditioner (rows == 0: none); exclusive with W
   double *Pu = nullptr;          // n: P u of the current PCG iteration
   int smem_x_elems = 0;          // doubles of dynamic shared memory for the staged slice
   int smem_rows = 0;             // doubles of dynamic shared memory for the row sums of a cluster pair (0: unpaired)
@@ -207,6 +225,7 @@ struct SolveCfg {
   // PCG controls (engine-specific; include/osqp_b200.h)
   double pcg_eta;          // PCG stops at |r|inf <= max(pcg_eta * |r0|inf, pcg_floor * |b|inf)
   double pcg_floor;
+  double pcg_eta_e;        // > 0: also continue while the last energy-norm decrement exceeds pcg_eta_e^2 of the total; < 0: automatic
   int pcg_max_iter;
   int refresh_every;       // recompute z_tilde = A x_tilde and r = b - K x_tilde every k ADMM iterations (1 = always)
   int wood_refresh;        // the Woodbury data (WoodDev C^{-1}, s, D) are stale: rebuild before the first PCG

@@ -779,7 +779,8 @@ __device__ __noinline__ double wood_apply(Grid &g, RedSmem &sm, const DevPtrs &d
 __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const DevPtrs &d, const PcgVecs &v,
                                     const double *rho_vec,
                                     const double *Minv, double sigma, double *xvec, double *zvec, double gamma,
-                                    double rn, double thresh, int max_it, int m0, int m1, int n0, int n1) {
+                                    double rn, double thresh, int max_it, int m0, int m1, int n0, int n1,
+                                    double thresh_floor = 0.0, double eta_e2 = 0.0) {
   const int tid = threadIdx.x, nth = blockDim.x;
   const int lanesA = d.A.lanes, lanesN = d.At.lanes;
   const int subA = tid & (lanesA - 1), grpA = tid / lanesA, ngrpA = nth / lanesA;
@@ -787,7 +788,12 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
   bool broke = false;
-  while (rn > thresh && it < max_it) {
+  // Second stopping rule (eta_e2 > 0): the energy-norm error of CG falls by alpha_k gamma_k per iteration
+  // (|e_k|_K^2 = |e_0|_K^2 - sum_{i<k} alpha_i gamma_i), so the solve also goes on while the last decrement is more
+  // than eta_e^2 of everything gained so far -- a residual that is small only because K is badly conditioned does
+  // not end the solve.  Below the round-off floor nothing goes on.
+  double esum = 0.0, elast = 0.0;
+  while (rn > thresh_floor && (rn > thresh || (eta_e2 > 0.0 && elast > eta_e2 * esum)) && it < max_it) {
     // ---- phase A: t = A uu, tr = rho .* t
     if (d.m > 0) {
       for (int base = m0; base < m1; base += ngrpA) {
@@ -870,6 +876,8 @@ __device__ __noinline__ int pcg_run(Grid &g, RedSmem &sm, PhaseClock &pc, const 
     gamma = red2[0];
     rn = red2[1];
     a_old = alpha;
+    elast = alpha * gamma_old;  // alpha_k gamma_k of the iteration just finished
+    esum += elast;
     it++;
   }
   return broke ? -(it + 1) : it;
@@ -898,14 +906,19 @@ __device__ __forceinline__ double part_sum(const TileStreamDev &T, int row) {
 __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, PhaseClock &pc, const DevPtrs &d,
                                            const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma, double *xvec,
                                            double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
-                                           int m1, int n0, int n1) {
+                                           int m1, int n0, int n1, double thresh_floor = 0.0, double eta_e2 = 0.0) {
   const bool wood = d.W.w > 0;  // Minv is then D^{-1} of the Woodbury preconditioner (wood_refresh, wood_apply)
   const int tid = threadIdx.x, nth = blockDim.x;
   const int m = d.m;
   double a_old = 1.0, gamma_old = 1.0;
   int it = 0;
   bool broke = false;
-  while (rn > thresh && it < max_it) {
+  // Second stopping rule (eta_e2 > 0): the energy-norm error of CG falls by alpha_k gamma_k per iteration
+  // (|e_k|_K^2 = |e_0|_K^2 - sum_{i<k} alpha_i gamma_i), so the solve also goes on while the last decrement is more
+  // than eta_e^2 of everything gained so far -- a residual that is small only because K is badly conditioned does
+  // not end the solve.  Below the round-off floor nothing goes on.
+  double esum = 0.0, elast = 0.0;
+  while (rn > thresh_floor && (rn > thresh || (eta_e2 > 0.0 && elast > eta_e2 * esum)) && it < max_it) {
     // beta only needs the gammas of the previous reductions
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     double red1[1] = {0.0};
@@ -1037,10 +1050,162 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     gamma = red2[0];
     rn = red2[1];
     a_old = alpha;
+    elast = alpha * gamma_old;  // alpha_k gamma_k of the iteration just finished
+    esum += elast;
     it++;
   }
   return broke ? -(it + 1) : it;
 }
+
+// ------------------------------------------------------------------ PCG with slack elimination in the preconditioner
+// (engine.cuh SlackDev).  Same Chronopoulos-Gear recurrences as pcg_run_stream; what differs is u = M^-1 r:
+//   G : slack rows i (column j):  g_i = rho_i a_ij r_j / K_yy,j                         (fp32 gather vector)   | barrier
+//   T2: stream A' against g  -> partials                                                                        | barrier
+//   U : x-part:  u_x = diag(S)^-1 (r_x - A_x' g),  gamma_x = r_x'u_x                  (Minv holds diag(S)^-1, 0 on Y) | barrier
+//   A : stream [A; P] against u_x (slack entries of the gather vector are zero); then per row
+//         slack row i:  u_j = (r_j - rho_i a_ij t_i) / K_yy,j ;  t_i += a_ij u_j      (u_y by back-substitution)
+//         all rows:     tr = rho .* t ;  delta = u'Pu + sigma |u|^2 + t'tr ;  gamma += r_y'u_y              | reduce + barrier
+//   B : stream A' against tr -> partials                                                                      | barrier
+//   V : w = Pu + sigma u + partials ;  p, s, x, r ;  Ap = t + beta Ap ;  z += alpha Ap ;  |r|inf            | reduce + barrier
+// The [A; P] phase of the preconditioner IS the A phase of the K-apply, so the preconditioner costs one extra A'
+// phase.  Not used by the polish (its penalties are not rho).
+__device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S, PhaseClock &pc, const DevPtrs &d,
+                                                 const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma,
+                                                 double *xvec, double *zvec, double rn, double thresh, int max_it, int m0,
+                                                 int m1, int n0, int n1, double thresh_floor = 0.0, double eta_e2 = 0.0) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const int m = d.m;
+  const SlackDev &L = d.SL;
+  double a_old = 1.0, gamma_old = 1.0;
+  int it = 0;
+  bool broke = false;
+  // per-row finish of the [A; P] phase (row sums complete): returns this row's share of {delta, gamma}
+  auto finish = [&](int r, double sum, double &dl, double &gm) {
+    if (r < m) {
+      double t = sum;
+      const int j = __ldg(L.col + r);
+      if (j >= 0) {
+        const double a = d.A.val[__ldg(L.pos + r)], ri = rho_vec[r], pjj = d.Pdiag[j];
+        const double kyy = pjj + sigma + ri * a * a;
+        const double rj = v.r[j];
+        const double uy = (rj - ri * a * t) / kyy;
+        v.uu[j] = uy;
+        d.Pu[j] = pjj * uy;
+        t = fma(a, uy, t);
+        dl += uy * (pjj * uy + sigma * uy);
+        gm += rj * uy;
+      }
+      const double tr = store_tr(d, v.tr, r, rho_vec[r] * t);
+      v.t[r] = t;
+      dl += t * tr;
+    } else {
+      const int j = r - m;
+      if (Minv[j] != 0.0) {  // x-part; the slack columns were handled by their rows
+        const double uj = v.uu[j];
+        d.Pu[j] = sum;
+        dl += uj * (sum + sigma * uj);
+      }
+    }
+  };
+  // Second stopping rule (eta_e2 > 0): the energy-norm error of CG falls by alpha_k gamma_k per iteration
+  // (|e_k|_K^2 = |e_0|_K^2 - sum_{i<k} alpha_i gamma_i), so the solve also goes on while the last decrement is more
+  // than eta_e^2 of everything gained so far -- a residual that is small only because K is badly conditioned does
+  // not end the solve.  Below the round-off floor nothing goes on.
+  double esum = 0.0, elast = 0.0;
+  while (rn > thresh_floor && (rn > thresh || (eta_e2 > 0.0 && elast > eta_e2 * esum)) && it < max_it) {
+    // ---- G
+    for (int i = m0 + tid; i < m1; i += nth) {
+      const int j = __ldg(L.col + i);
+      if (j >= 0) {
+        const double a = d.A.val[__ldg(L.pos + i)], ri = rho_vec[i];
+        const double kyy = d.Pdiag[j] + sigma + ri * a * a;
+        L.g32[i] = (float)(ri * a * v.r[j] / kyy);
+      }
+    }
+    grid_barrier(g);
+    // ---- T2
+    stream_phase_f32(S, d.ST, L.g32);
+    grid_barrier(g);
+    // ---- U
+    double red[2] = {0.0, 0.0};  // delta, gamma
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double mj = Minv[j];
+      if (mj != 0.0) {
+        const double rj = v.r[j];
+        const double uj = store_u(d, v.uu, j, mj * (rj - part_sum(d.ST, j)));
+        red[1] += rj * uj;
+      }
+    }
+    stream_prefetch_head(d.SA);
+    grid_barrier(g);
+    pc.tick(7);
+    // ---- A
+    if (d.SA.paired) {
+      auto fin = [&](int r, double sum) { finish(r, sum, red[0], red[1]); };
+      stream_phase_paired<true>(S, d.SA, d.uu32, fin);
+      pc.tick(0);
+    } else {
+      stream_phase_f32(S, d.SA, d.uu32);
+      pc.tick(0);
+      grid_barrier(g);
+      pc.tick(1);
+      for (int i = m0 + tid; i < m1; i += nth) finish(i, part_sum(d.SA, i), red[0], red[1]);
+      for (int j = n0 + tid; j < n1; j += nth) finish(m + j, part_sum(d.SA, m + j), red[0], red[1]);
+    }
+    stream_prefetch_head(d.ST);
+    pc.tick(2);
+    reduce_and_barrier<2>(g, sm, red, 0u);
+    pc.tick(3);
+    const double delta = red[0], gamma = red[1];
+    const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
+    // ---- B
+    stream_phase_f32(S, d.ST, d.tr32);
+    stream_prefetch_head(d.SA);
+    pc.tick(4);
+    grid_barrier(g);
+    pc.tick(5);
+    const double denom = (it == 0) ? delta : delta - beta * gamma / a_old;
+    const double alpha = gamma / denom;
+    if (!(alpha > 0.0) || !isfinite(alpha)) {
+      broke = pcg_negative_curvature(delta, denom);
+      break;
+    }
+    // ---- V
+    double red2[1] = {0.0};
+    for (int j = n0 + tid; j < n1; j += nth) {
+      const double uj = v.uu[j];
+      const double wj = d.Pu[j] + sigma * uj + part_sum(d.ST, j);
+      const double pj = (it > 0) ? uj + beta * v.p[j] : uj;
+      const double sj = (it > 0) ? wj + beta * v.s[j] : wj;
+      v.p[j] = pj;
+      v.s[j] = sj;
+      xvec[j] += alpha * pj;
+      const double rj = v.r[j] - alpha * sj;
+      v.r[j] = rj;
+      red2[0] = fmax(red2[0], fabs(rj));
+    }
+    if (zvec != nullptr)
+      for (int i = m0 + tid; i < m1; i += nth) {
+        const double api = (it > 0) ? v.t[i] + beta * v.Ap[i] : v.t[i];
+        v.Ap[i] = api;
+        zvec[i] += alpha * api;
+      }
+    pc.tick(6);
+    reduce_and_barrier<1>(g, sm, red2, 0x1u);
+    gamma_old = gamma;
+    rn = red2[0];
+    a_old = alpha;
+    elast = alpha * gamma_old;  // alpha_k gamma_k of the iteration just finished
+    esum += elast;
+    it++;
+  }
+  return broke ? -(it + 1) : it;
+}
+
+// Data of the slack preconditioner for the current rho: reduced weights, diag(S)^-1 (zero on the slack columns), and a
+// clean fp32 gather copy of u on the slack columns.  Entered and left by every thread of the grid.
+__device__ __noinline__ void slack_refresh(Grid &g, const DevPtrs &d, const double *rho_vec, double sigma, double *Minv,
+                                           int m0, int m1, int n0, int n1);
 
 // ------------------------------------------------------------------ update_info (row a9) + infeasibility products (row a10)
 // One phase streams A, P and A' once each with two gathered vectors per matrix:
@@ -1243,6 +1408,35 @@ __device__ __forceinline__ void precond_rows(const DevPtrs &d, const double *rho
     group_reduce<1>(acc, lanesN);
     if (valid && subN == 0) Minv[row] = 1.0 / (d.Pdiag[row] + sigma + acc.a[0]);
   }
+}
+
+__device__ __noinline__ void slack_refresh(Grid &g, const DevPtrs &d, const double *rho_vec, double sigma, double *Minv,
+                                           int m0, int m1, int n0, int n1) {
+  const int tid = threadIdx.x, nth = blockDim.x;
+  const SlackDev &L = d.SL;
+  grid_barrier(g);  // rho_vec is complete
+  for (int i = m0 + tid; i < m1; i += nth) {
+    const int j = L.col[i];
+    double re = rho_vec[i];
+    if (j >= 0) {
+      const double a = d.A.val[L.pos[i]], pj = d.Pdiag[j] + sigma;
+      re = re * pj / (pj + re * a * a);
+    } else {
+      L.g32[i] = 0.0f;
+    }
+    L.rho_eff[i] = re;
+  }
+  grid_barrier(g);
+  precond_rows(d, L.rho_eff, sigma, Minv, n0, n1);
+  grid_barrier(g);
+  for (int i = m0 + tid; i < m1; i += nth) {
+    const int j = L.col[i];
+    if (j >= 0) {
+      Minv[j] = 0.0;      // marks the slack columns for pcg_run_stream_slack
+      d.uu32[j] = 0.0f;   // and they never enter the gathered u
+    }
+  }
+  grid_barrier(g);
 }
 
 // ------------------------------------------------------------------ Woodbury part of the preconditioner (engine.cuh WoodDev)
@@ -1465,7 +1659,9 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   grid_barrier(g);
 
   const bool wood = d.blocked && d.W.w > 0;
+  const bool slack = d.blocked && d.SL.rows > 0;
   if (wood && c.wood_refresh) wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+  if (slack && c.wood_refresh) slack_refresh(g, d, d.rho_vec, c.sigma, d.Minv, m0, m1, n0, n1);
 
   InfoScalars S;
   S.pri_res = S.dua_res = S.obj_val = 0.0;
@@ -1519,7 +1715,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
         d.r[j] = rj;
         double uj = d.Minv[j] * rj;
         if (wood) d.W.v[j] = uj;
-        else uj = store_u(d, d.uu, j, uj);
+        else if (!slack) uj = store_u(d, d.uu, j, uj);  // slack mode: u is formed at the top of the PCG iteration
         red3[0] += rj * uj;
         red3[1] = fmax(red3[1], fabs(rj));
         red3[2] = fmax(red3[2], fabs(bj));
@@ -1553,7 +1749,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
         d.r[row] = rj;
         double uj = d.Minv[row] * rj;
         if (wood) d.W.v[row] = uj;
-        else uj = store_u(d, d.uu, row, uj);
+        else if (!slack) uj = store_u(d, d.uu, row, uj);
         red3[0] += rj * uj;
         red3[1] = fmax(red3[1], fabs(rj));
         red3[2] = fmax(red3[2], fabs(bj));
@@ -1572,10 +1768,18 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       // stop when the residual has dropped by pcg_eta relative to where this ADMM step started
       // (r0 measures how far the system moved since the last solve), floored at roundoff level
       const double thresh = fmax(c.pcg_eta * red3[1], c.pcg_floor * red3[2]);
-      int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
-                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
+      // the energy-norm rule rides on gamma = r'M^-1 r, which measures the error only when M is close to K: on by default
+      // (eta_e = 1e-3) with the slack-elimination preconditioner, where it restores the oracle's iteration counts on the
+      // Lasso config at no extra PCG iterations; off with plain Jacobi, where it costs 26 % more PCG iterations on config 2
+      // for no change in parity, and with the Woodbury correction (M = K on the portfolio: one iteration is exact)
+      const double ee = c.pcg_eta_e >= 0.0 ? c.pcg_eta_e : (slack ? 1e-3 : 0.0);
+      const double tfl = c.pcg_floor * red3[2], ee2 = ee * ee;
+      int ncg = slack     ? pcg_run_stream_slack(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[1],
+                                                 thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
+                : d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
                           : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
-                                    thresh, c.pcg_max_iter, m0, m1, n0, n1);
+                                    thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2);
       if (ncg < 0) {  // K = P + sigma I + A' rho A has a direction of non-positive curvature (uniform over the grid)
         ncg = -ncg - 1;
         pcg_broke = true;
@@ -1673,6 +1877,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
         }
         if (wood) {
           wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
+        } else if (slack) {
+          slack_refresh(g, d, d.rho_vec, c.sigma, d.Minv, m0, m1, n0, n1);
         } else {
           grid_barrier(g);
           precond_rows(d, d.rho_vec, c.sigma, d.Minv, n0, n1);

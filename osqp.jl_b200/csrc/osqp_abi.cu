@@ -69,7 +69,7 @@ struct Engine {
   long long *stage_idx = nullptr;
   long long stage_cap = 0;
   // engine controls
-  double pcg_eta = 1e-3, pcg_floor = 1e-13;
+  double pcg_eta = 1e-3, pcg_floor = 1e-13, pcg_eta_e = -1.0;  // pcg_eta_e < 0: automatic (kernels.cu admm_kernel)
   int pcg_max_iter = 0, refresh_every = 25;
   double polish_penalty = 1e4;
   bool first_run = true, clear_update_time = false;
@@ -1142,6 +1142,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
   e.st = *settings;
   e.pcg_eta = env_double("OSQP_B200_PCG_ETA", e.pcg_eta);
   e.pcg_floor = env_double("OSQP_B200_PCG_FLOOR", e.pcg_floor);
+  e.pcg_eta_e = env_double("OSQP_B200_PCG_ETA_E", e.pcg_eta_e);
   e.refresh_every = env_int("OSQP_B200_REFRESH_EVERY", e.refresh_every);
   e.polish_penalty = env_double("OSQP_B200_POLISH_PENALTY", e.polish_penalty);
   const int n = (int)data->n, m = (int)data->m;
@@ -1477,6 +1478,41 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     }
   }
 
+  // ---- slack elimination in the preconditioner (engine.cuh SlackDev): equality rows with a private slack column,
+  // when they are too many for the Woodbury correction
+  if (d.blocked && m > 0 && d.W.w == 0 && env_int("OSQP_B200_SLACK", 1) != 0) {
+    std::vector<int> scol(m, -1), spos(m, -1);
+    int cnt = 0;
+    for (int j = 0; j < n; j++) {
+      if (At_rowptr[j + 1] - At_rowptr[j] != 1) continue;
+      bool pdiag = true;
+      for (int k = P_rowptr[j]; k < P_rowptr[j + 1] && pdiag; k++) pdiag = P_col[k] == j;
+      if (!pdiag) continue;
+      const int i = At_col[At_rowptr[j]];
+      if (data->u[i] - data->l[i] < 1e-4 && scol[i] < 0 && A_rowptr[i + 1] - A_rowptr[i] >= 2) {
+        scol[i] = j;
+        spos[i] = mapA[At_rowptr[j]];
+        cnt++;
+      }
+    }
+    if (cnt >= 256) {
+      SlackDev &S = d.SL;
+      CU_OK(dalloc(e, &S.col, (size_t)m)); CU_OK(dalloc(e, &S.pos, (size_t)m));
+      CU_OK(dalloc(e, &S.rho_eff, (size_t)m + 8)); CU_OK(dalloc(e, &S.g32, (size_t)m + 32));
+      CU_OK(cudaMemcpyAsync(S.col, scol.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+      CU_OK(cudaMemcpyAsync(S.pos, spos.data(), (size_t)m * sizeof(int), cudaMemcpyHostToDevice, e.stream));
+      CU_OK(cudaStreamSynchronize(e.stream));
+      S.rows = cnt;
+      if (!d.f32_slices) {  // the extra phase gathers an fp32 vector
+        d.f32_slices = 1;
+        CU_OK(dalloc(e, &d.uu32, (size_t)n + 32));
+        CU_OK(dalloc(e, &d.tr32, (size_t)m + 32));
+      }
+      if (env_int("OSQP_B200_DEBUG", 0))
+        fprintf(stderr, "[osqp_b200] slack elimination in the preconditioner: %d equality rows with a private column\n", cnt);
+    }
+  }
+
   mark("tile streams (host build + upload)");
   // ---- state, scaling (a2), rho vector (a3), preconditioner, convexity probe
   e.st.rho = std::min(std::max(e.st.rho, kRhoMin), kRhoMax);
@@ -1579,9 +1615,9 @@ static c_int solve_impl(Engine &e) {
   c.warm_start = (int)e.st.warm_start; c.verbose = (int)e.st.verbose;
   const double base = e.first_run ? e.info.setup_time : e.info.update_time;
   c.time_limit_s = e.st.time_limit > 0 ? e.st.time_limit - base : -1e30;
-  c.pcg_eta = e.pcg_eta; c.pcg_floor = e.pcg_floor; c.pcg_max_iter = e.pcg_max_iter;
+  c.pcg_eta = e.pcg_eta; c.pcg_floor = e.pcg_floor; c.pcg_eta_e = e.pcg_eta_e; c.pcg_max_iter = e.pcg_max_iter;
   c.refresh_every = e.refresh_every;
-  c.wood_refresh = (e.d.W.w > 0 && e.wood_dirty) ? 1 : 0;
+  c.wood_refresh = ((e.d.W.w > 0 || e.d.SL.rows > 0) && e.wood_dirty) ? 1 : 0;
   if (e.st.verbose) printf("iter   objective    pri res    dua res    rho        time\n");
   // Automatic adaptive-rho interval (settings.adaptive_rho_interval = 0).  libosqp derives it from wall-clock:
   // the first iteration after 0.4 * setup_time, rounded to a multiple of check_termination -- a trade between the
@@ -1646,6 +1682,7 @@ static c_int solve_impl(Engine &e) {
     const double vn = 8.0 * n, vm = 8.0 * m;
     e.prof.alg_bytes = k * (bA + bAt + bP + 11 * vn + 5 * vm) + it * (bAt + 6 * vn + 12 * vm + 4 * vn) +
                        rf * (bA + bP) + ck * (bA + bAt + bP);
+    if (e.d.SL.rows > 0) e.prof.alg_bytes += k * (bAt + 2 * vn + 2 * vm);  // the extra A' phase of the slack preconditioner
   }
   if (e.st.verbose) {
     for (long long r = 0; r < I.log_rows; r++)

@@ -38,9 +38,13 @@ def test_lasso_lambda_sweep_warm_started(pkg, engine_lib, oracle_lib, n_feat, n_
         assert e.info.status == o.info.status == "Solved", (lam, e.info.status, o.info.status)
         # same optimum: objective and solution within the solver's tolerance (rho adapts, so iteration counts of
         # the two linear-system backends may differ by an adaptive-rho interval)
-        assert abs(e.info.obj_val - o.info.obj_val) <= 20 * eps * (1 + abs(o.info.obj_val)), lam
-        assert np.max(np.abs(e.x - o.x)) <= 20 * eps * (1 + np.max(np.abs(o.x))), lam
-        assert abs(e.info.iter - o.info.iter) <= 50, (lam, e.info.iter, o.info.iter)
+        # the 1000 x 5000 case runs on the tile streams with the slack-elimination preconditioner and follows the oracle to
+        # one check interval; the small case runs Jacobi-PCG on the CSR path, whose inexact solves on this badly
+        # conditioned K cost up to two intervals (round-1 tolerances)
+        xtol, itol = (10, 25) if n_feat >= 1000 else (20, 50)
+        assert abs(e.info.obj_val - o.info.obj_val) <= xtol * eps * (1 + abs(o.info.obj_val)), lam
+        assert np.max(np.abs(e.x - o.x)) <= xtol * eps * (1 + np.max(np.abs(o.x))), lam
+        assert abs(e.info.iter - o.info.iter) <= itol, (lam, e.info.iter, o.info.iter)
         prev_iters = e.info.iter
     # at lambda_max the Lasso solution is x = 0
     assert prev_iters is not None
@@ -127,3 +131,48 @@ def test_portfolio_woodbury_preconditioner(pkg, engine_lib, oracle_lib):
     assert k_per_it["woodbury"] <= 5.0, k_per_it
     assert k_per_it["jacobi"] >= 4 * k_per_it["woodbury"], k_per_it
     assert polish_ms["woodbury"] < polish_ms["jacobi"], polish_ms
+
+
+def test_lasso_slack_elimination_preconditioner(pkg, engine_lib, oracle_lib):
+    # The 5000 equality rows  Ad x - y = b  of the Lasso QP each own a slack column: eliminating those columns inside
+    # the preconditioner (engine.cuh SlackDev) must leave the ADMM trajectory alone -- same status, rho updates,
+    # iteration count and solution as the oracle and as plain Jacobi -- at a fraction of the PCG iterations.
+    import ctypes as C
+    import os
+
+    prob, lam_max, q_of, n = problems.lasso_c3(1000, 5000, 0.15, 20263)
+    prob = dict(prob, q=q_of(0.1 * lam_max))
+    eps = 1e-5
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=10000, polish=False)
+    eng = pkg.load_library(engine_lib)
+    res, k_per_it = {}, {}
+    for name in ("slack", "jacobi"):
+        os.environ["OSQP_B200_SLACK"] = "1" if name == "slack" else "0"
+        try:
+            mdl = pkg.Model(lib=engine_lib)
+            mdl.setup(**prob, **opts)
+        finally:
+            os.environ.pop("OSQP_B200_SLACK", None)
+        res[name] = mdl.solve()
+        prof = pkg.types.B200Profile()
+        assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
+        assert int(prof.streams) == 1
+        k_per_it[name] = prof.pcg_iters / max(1, prof.admm_iters)
+        mdl.clean()
+    mo = pkg.Model(lib=oracle_lib)
+    mo.setup(**prob, **opts)
+    o = mo.solve()
+    mo.clean()
+    s, j = res["slack"], res["jacobi"]
+    assert s.info.status == j.info.status == o.info.status == "Solved"
+    # with the slack preconditioner (and the energy-norm stopping rule that comes with it) the engine follows the oracle:
+    # same rho updates, same check at which the solve ends, solution within a few eps
+    assert s.info.rho_updates == o.info.rho_updates
+    assert abs(s.info.iter - o.info.iter) <= 25, (s.info.iter, o.info.iter)
+    assert np.max(np.abs(s.x - o.x)) <= 5 * eps * (1 + np.max(np.abs(o.x)))
+    assert abs(s.info.obj_val - o.info.obj_val) <= 5 * eps * (1 + abs(o.info.obj_val))
+    # plain Jacobi with the residual rule reaches the same optimum more slowly on this badly conditioned K (round 1's path)
+    assert np.max(np.abs(j.x - o.x)) <= 50 * eps * (1 + np.max(np.abs(o.x)))
+    assert j.info.iter >= s.info.iter
+    assert k_per_it["slack"] <= 15.0, k_per_it
+    assert k_per_it["jacobi"] >= 2.0 * k_per_it["slack"], k_per_it
