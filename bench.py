@@ -662,9 +662,16 @@ def main():
             "value": s["value"], "ms_per_step": s["ms_per_step"], "scaling": "strong",
             "e2e": {"value": s["e2e"], "unit": UNIT, "h2d_bytes_per_step": b["h2d"], "d2h_bytes_per_step": b["d2h"]},
             "gpu_launches": 2 * args.steps,
-            "roofline": {"bound": "hbm", "kernel": "batch_fast_solve_kernel", "achieved": None, "peak": peak,
-                         "unit": "GB/s", "frac": None, "peak_source": peak_src, "traffic": None,
-                         "note": "latency / FP64-issue bound: the per-QP working set never leaves the SM (DESIGN.md 7)"},
+            # HBM is touched once per solve: the per-QP state comes in (values, inverse factor, vectors: 12.8 KB for the
+            # 30 x 60 MPC QP) and x*, y*, info and the iterates go out (1.1 KB) -- 13.9 KB per QP measured by ncu
+            # (profiles/r2_ncu_batch.md: 104.7 MB read + 8.9 MB written per 8192-QP launch)
+            "roofline": {"bound": "hbm", "kernel": "batch_fast_solve_kernel",
+                         "achieved": 13.9e3 * b["qps_per_gpu"] / (b["kern_ms"] / args.steps * 1e-3) / 1e9 if b["kern_ms"] > 0 else None,
+                         "peak": peak, "unit": "GB/s",
+                         "frac": 13.9e3 * b["qps_per_gpu"] / (b["kern_ms"] / args.steps * 1e-3) / 1e9 / peak if b["kern_ms"] > 0 else None,
+                         "peak_source": peak_src, "traffic": 113.6e6 * b["qps_per_gpu"] / 8192.0,
+                         "note": "per GPU; latency / issue bound, not HBM bound: the per-QP working set lives in shared "
+                                 "memory and registers for the whole solve (DESIGN.md 7)"},
             "cpu_baseline": cpu, "clocks": clocks, "batch": s, **extras})
     if D.rank == 0:
         emit(line)

@@ -503,6 +503,17 @@ bool build_tile_stream(const std::vector<CsrRef> &mats, int cols, int grid, int 
       }
     }
     T.w_s0[(size_t)grid * kWarps] = (int)T.sl_len.size();
+    if (dbg) {  // how well the slices fill the warps: slowest warp of a block against the block's mean, and block against grid
+      double worst = 0.0, sum_max = 0.0, gmax = 0.0, gsum = 0.0;
+      for (int b = 0; b < grid; b++) {
+        long long tot = 0, mx = 0;
+        for (int w = 0; w < kWarps; w++) { const long long q = T.w_qn[(size_t)b * kWarps + w]; tot += q; mx = std::max(mx, q); }
+        const double r = tot > 0 ? (double)mx * kWarps / (double)tot : 1.0;
+        worst = std::max(worst, r); sum_max += r; gmax = std::max(gmax, (double)mx); gsum += (double)mx;
+      }
+      fprintf(stderr, "[osqp_b200]   lane rows: slowest warp / mean warp of a block: avg %.3f worst %.3f; slowest block / mean block %.3f\n",
+              sum_max / grid, worst, gmax * grid / std::max(1.0, gsum));
+    }
     // Few stream rows per block (or wildly different lengths inside a slice) leave lanes idle: past 25 % more stored
     // entries than the scan layout needs, use the scan layout
     if ((double)pos > 1.25 * (double)stored) {

@@ -442,3 +442,26 @@ def test_two_models_with_different_slices_coexist(pkg, engine_lib):
     assert r1b.info.iter <= r1.info.iter  # warm-started from the solution
     m1.clean()
     m2.clean()
+
+
+def test_tiny_mode_settings_variants_match_oracle(pkg, engine_lib, oracle_lib):
+    # n, m <= 256: the workspace also lives in the batched engine and is solved there; the settings
+    # that change the arithmetic must reach it
+    prob = random_qp(60, 90, 0.15, 31)
+    eng = pkg.load_library(engine_lib)
+    for extra in (dict(), dict(scaling=0), dict(scaled_termination=1), dict(alpha=1.0), dict(sigma=1e-3, rho=1.0),
+                  dict(adaptive_rho=True, adaptive_rho_interval=25, check_termination=25)):
+        opts = dict(FIXED_RHO, eps_abs=1e-6, eps_rel=1e-6)
+        opts.update(extra)
+        r = solve_both(pkg, engine_lib, oracle_lib, prob, opts)
+        assert_parity(r["engine"][1], r["oracle"][1], 1e-6, iter_tol=25 if extra.get("adaptive_rho") else 1)
+        prof = pkg.types.B200Profile()
+        assert eng.osqp_b200_get_profile(r["engine"][0].workspace, C.byref(prof)) == 0
+        assert int(prof.pcg_iters) == 0 and int(prof.admm_iters) == r["engine"][1].info.iter  # solved by the tiny engine
+    # polish needs the general engine: the solve switches over, warm-started from the tiny engine's solution
+    mdl = r["engine"][0]
+    mdl.update_settings(polish=True)
+    rp = mdl.solve()
+    assert rp.info.status == "Solved" and rp.info.status_polish in (1, -1)
+    assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0 and int(prof.pcg_iters) > 0
+    assert np.max(np.abs(rp.x - r["oracle"][1].x)) <= 1e-5 * (1 + np.max(np.abs(rp.x)))
