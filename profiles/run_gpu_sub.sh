@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-(timeout 100 python profiles/batch_driver.py 1024 250 2>&1 | tail -1)
-(timeout 100 python profiles/batch_driver.py 148 250 2>&1 | tail -1)
-(timeout 300 ncu --set full --import-source on --clock-control none -k regex:batch_fast_solve -c 1 -o gpurun_out/batch_lat python profiles/batch_driver.py 1024 250 2>&1 | tail -2)
+for F in 1 0 1 0; do echo "== f32 slices $F"; (OSQP_B200_F32_SLICES=$F timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -3); done
