@@ -1,2 +1,2 @@
 mkdir -p gpurun_out
-for F in 1 0 1 0; do echo "== f32 slices $F"; (OSQP_B200_F32_SLICES=$F timeout 120 python profiles/profile_driver.py --solves 2 2>&1 | grep -v "^spmv" | tail -3); done
+(timeout 900 python -m pytest tests/test_configs.py -m gpu -q -x -k "follows" --durations=3 2>&1 | tail -25)

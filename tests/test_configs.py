@@ -176,3 +176,92 @@ def test_lasso_slack_elimination_preconditioner(pkg, engine_lib, oracle_lib):
     assert j.info.iter >= s.info.iter
     assert k_per_it["slack"] <= 15.0, k_per_it
     assert k_per_it["jacobi"] >= 2.0 * k_per_it["slack"], k_per_it
+
+
+def _oracle_fresh(pkg, oracle_lib, prob, opts):
+    mo = pkg.Model(lib=oracle_lib)
+    mo.setup(**prob, **opts)
+    r = mo.solve()
+    mo.clean()
+    return r
+
+
+def test_woodbury_follows_bound_rho_and_matrix_updates(pkg, engine_lib, oracle_lib):
+    # The membership of the Woodbury set is fixed at setup; the data in it is not: bounds that turn coupling equalities
+    # into inequalities (their rho class changes), osqp_update_rho and osqp_update_A must all reach the preconditioner
+    # (C, C^-1 are rebuilt by the next launch) -- the results must match a fresh oracle setup of the updated problem.
+    import os
+
+    n_assets = 4000
+    prob = problems.portfolio_c4(n_assets, n_assets // 100, 20264)
+    eps = 1e-5
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=20000, polish=False)
+    os.environ["OSQP_B200_STREAM_MIN_NNZ"] = "50000"
+    try:
+        mdl = pkg.Model(lib=engine_lib)
+        mdl.setup(**prob, **opts)
+    finally:
+        os.environ.pop("OSQP_B200_STREAM_MIN_NNZ", None)
+    r0 = mdl.solve()
+    assert r0.info.status == "Solved"
+    k = n_assets // 100
+    # (1) relax the factor equalities y = F'x into |y - F'x| <= 0.05, keep the budget row
+    l, u = prob["l"].copy(), prob["u"].copy()
+    l[:k] -= 0.05
+    u[:k] += 0.05
+    mdl.update(l=l, u=u)
+    mdl.update_settings(rho=0.1)  # the first solve adapted rho: start where a fresh setup starts
+    mdl.warm_start(x=np.zeros(prob["P"].shape[0]), y=np.zeros(prob["A"].shape[0]))
+    r1 = mdl.solve()
+    o1 = _oracle_fresh(pkg, oracle_lib, dict(prob, l=l, u=u), opts)
+    assert r1.info.status == o1.info.status == "Solved"
+    assert abs(r1.info.iter - o1.info.iter) <= 25, (r1.info.iter, o1.info.iter)
+    assert abs(r1.info.obj_val - o1.info.obj_val) <= 10 * eps * (1 + abs(o1.info.obj_val))
+    assert np.max(np.abs(r1.x - o1.x)) <= 10 * eps * (1 + np.max(np.abs(o1.x)))
+    # (2) a new rho, (3) new values in A (the factor loadings of the first 50 assets doubled)
+    mdl.update_settings(rho=0.5)
+    A2 = prob["A"].copy().tocsc()
+    A2.data = A2.data.copy()
+    for j in range(50):
+        sl = slice(A2.indptr[j], A2.indptr[j + 1])
+        rows = A2.indices[sl]
+        A2.data[sl] = np.where(rows < k, 2.0 * A2.data[sl], A2.data[sl])
+    mdl.update(Ax=A2.data)
+    mdl.warm_start(x=np.zeros(prob["P"].shape[0]), y=np.zeros(prob["A"].shape[0]))
+    r2 = mdl.solve()
+    o2 = _oracle_fresh(pkg, oracle_lib, dict(prob, A=A2, l=l, u=u), dict(opts, rho=0.5))
+    assert r2.info.status == o2.info.status == "Solved"
+    assert abs(r2.info.iter - o2.info.iter) <= 25, (r2.info.iter, o2.info.iter)
+    assert abs(r2.info.obj_val - o2.info.obj_val) <= 10 * eps * (1 + abs(o2.info.obj_val))
+    assert np.max(np.abs(r2.x - o2.x)) <= 10 * eps * (1 + np.max(np.abs(o2.x)))
+    mdl.clean()
+
+
+def test_slack_preconditioner_follows_matrix_and_bound_updates(pkg, engine_lib, oracle_lib):
+    # Lasso on the tile streams with the slack-elimination preconditioner: new data values (osqp_update_A on A_d) and a
+    # new right-hand side b (osqp_update_bounds) must give what a fresh oracle setup of the updated problem gives
+    prob, lam_max, q_of, n = problems.lasso_c3(1000, 5000, 0.15, 20263)
+    prob = dict(prob, q=q_of(0.2 * lam_max))
+    eps = 1e-5
+    opts = dict(verbose=False, eps_abs=eps, eps_rel=eps, adaptive_rho_interval=25, max_iter=10000, polish=False)
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, **opts)
+    assert mdl.solve().info.status == "Solved"
+    rng = np.random.default_rng(3)
+    A2 = prob["A"].copy().tocsc()
+    A2.data = A2.data * (1.0 + 0.1 * rng.standard_normal(A2.nnz) * (np.abs(A2.data) != 1.0))  # leave the identity blocks
+    l, u = prob["l"].copy(), prob["u"].copy()
+    shift = 0.05 * rng.standard_normal(5000)
+    l[:5000] += shift
+    u[:5000] += shift
+    mdl.update(Ax=A2.data)
+    mdl.update(l=l, u=u)
+    mdl.update_settings(rho=0.1)  # the first solve adapted rho: start where a fresh setup starts
+    mdl.warm_start(x=np.zeros(n), y=np.zeros(prob["A"].shape[0]))
+    r = mdl.solve()
+    o = _oracle_fresh(pkg, oracle_lib, dict(prob, A=A2, l=l, u=u), opts)
+    assert r.info.status == o.info.status == "Solved"
+    assert r.info.rho_updates == o.info.rho_updates
+    assert abs(r.info.iter - o.info.iter) <= 25, (r.info.iter, o.info.iter)
+    assert np.max(np.abs(r.x - o.x)) <= 10 * eps * (1 + np.max(np.abs(o.x)))
+    mdl.clean()
