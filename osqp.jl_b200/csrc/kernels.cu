@@ -21,6 +21,18 @@
 #include <mutex>
 #include <utility>
 
+// This file is compiled TWICE.  The plain compilation holds every kernel and decides the storage mode of a workspace
+// at run time (CSR or tile streams, scan or lane-row layout, cluster pairs or not, fp64 or fp32 slices, Jacobi /
+// Woodbury / slack-elimination preconditioner).  kernels_fast.cu includes it again with OSQP_B200_FAST defined: the
+// same admm_kernel / polish_kernel with the mode of the common large sparse problem (fast_mode() below) fixed at
+// compile time.  Less than half the code and fewer spills: measured 5 % faster on every phase of config 2
+// (profiles/r2_ncu_admm.md section 5).  MODE(x, v) is x in the plain compilation and the constant v in the fast one.
+#ifdef OSQP_B200_FAST
+#define MODE(x, v) (v)
+#else
+#define MODE(x, v) (x)
+#endif
+
 namespace osqpb200 {
 
 namespace {
@@ -98,7 +110,7 @@ __device__ __forceinline__ void slice_init(Slice &S, const DevPtrs &d) {
   S.mbar = S.ys + 8u * (unsigned)d.smem_rows;
   S.parity = 0;
   S.probe = nullptr;
-  if (d.blocked) {
+  if (MODE(d.blocked, 1)) {
     if (threadIdx.x == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(S.mbar));
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -466,11 +478,11 @@ __device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, c
 }
 
 __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, const double *__restrict__ vec) {
-  if (T.lane_rows) stream_phase_lr<kDepthLR, false, false>(S, T, vec);
+  if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, false, false>(S, T, vec);
   else stream_phase_impl<kDepth, false, false>(S, T, vec);
 }
 __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &T, const float *__restrict__ vec) {
-  if (T.lane_rows) stream_phase_lr<kDepthLR, false, true>(S, T, vec);
+  if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, false, true>(S, T, vec);
   else stream_phase_impl<kDepth, false, true>(S, T, vec);
 }
 
@@ -482,7 +494,7 @@ __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &
 template <bool kF32 = false, typename Fin>
 __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const void *__restrict__ vec,
                                                     Fin fin) {
-  if (T.lane_rows) stream_phase_lr<kDepthLR, true, kF32>(S, T, vec);
+  if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, true, kF32>(S, T, vec);
   else stream_phase_impl<kDepth, true, kF32>(S, T, vec);
   cluster_sync();
   const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
@@ -754,7 +766,7 @@ struct PcgVecs {
 // u = M^{-1} r and tr = rho .* (A u) as the PCG phases gather them: with fp32 slices the value is rounded to fp32 ONCE,
 // here, and the rounded value is what every recurrence and dot product sees (engine.cuh DevPtrs::f32_slices).
 __device__ __forceinline__ double store_u(const DevPtrs &d, double *uvec, int j, double u) {
-  if (d.f32_slices) {
+  if (MODE(d.f32_slices, 1)) {
     const float f = (float)u;
     d.uu32[j] = f;
     u = (double)f;
@@ -763,7 +775,7 @@ __device__ __forceinline__ double store_u(const DevPtrs &d, double *uvec, int j,
   return u;
 }
 __device__ __forceinline__ double store_tr(const DevPtrs &d, double *trvec, int i, double tr) {
-  if (d.f32_slices) {
+  if (MODE(d.f32_slices, 1)) {
     const float f = (float)tr;
     d.tr32[i] = f;
     tr = (double)f;
@@ -907,7 +919,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
                                            const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma, double *xvec,
                                            double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
                                            int m1, int n0, int n1, double thresh_floor = 0.0, double eta_e2 = 0.0) {
-  const bool wood = d.W.w > 0;  // Minv is then D^{-1} of the Woodbury preconditioner (wood_refresh, wood_apply)
+  const bool wood = MODE(d.W.w > 0, false);  // Minv is then D^{-1} of the Woodbury preconditioner (wood_refresh, wood_apply)
   const int tid = threadIdx.x, nth = blockDim.x;
   const int m = d.m;
   double a_old = 1.0, gamma_old = 1.0;
@@ -922,7 +934,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     // beta only needs the gammas of the previous reductions
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     double red1[1] = {0.0};
-    if (d.SA.paired) {
+    if (MODE(d.SA.paired, 1)) {
       // ---- phase A with the combine fused in (cluster pairs): no partials, no extra grid barrier
       const bool rec = zvec != nullptr && it > 0;
       auto fin = [&](int r, double sum) {
@@ -936,13 +948,13 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
           red1[0] += uj * (sum + sigma * uj);
         }
       };
-      if (d.f32_slices) stream_phase_paired<true>(S, d.SA, d.uu32, fin);
+      if (MODE(d.f32_slices, 1)) stream_phase_paired<true>(S, d.SA, d.uu32, fin);
       else stream_phase_paired<false>(S, d.SA, v.uu, fin);
       if (m > 0) stream_prefetch_head(d.ST);
       pc.tick(0);
     } else {
     // ---- phase A
-    if (d.f32_slices) stream_phase_f32(S, d.SA, d.uu32);
+    if (MODE(d.f32_slices, 1)) stream_phase_f32(S, d.SA, d.uu32);
     else stream_phase(S, d.SA, v.uu);
     if (m > 0) stream_prefetch_head(d.ST);
     pc.tick(0);
@@ -983,7 +995,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       reduce_and_barrier_fx<1>(g, sm, red1, 0u, gamma);  // delta / gamma is a Rayleigh quotient of M^-1 K
       pc.tick(3);
       // ---- phase B
-      if (d.f32_slices) stream_phase_f32(S, d.ST, d.tr32);
+      if (MODE(d.f32_slices, 1)) stream_phase_f32(S, d.ST, d.tr32);
       else stream_phase(S, d.ST, v.tr);
       stream_prefetch_head(d.SA);
       pc.tick(4);
@@ -1140,7 +1152,7 @@ __device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S,
     grid_barrier(g);
     pc.tick(7);
     // ---- A
-    if (d.SA.paired) {
+    if (MODE(d.SA.paired, 1)) {
       auto fin = [&](int r, double sum) { finish(r, sum, red[0], red[1]); };
       stream_phase_paired<true>(S, d.SA, d.uu32, fin);
       pc.tick(0);
@@ -1312,7 +1324,7 @@ __device__ __noinline__ void compute_info_stream(Grid &g, RedSmem &sm, Slice &SG
   const bool unscale = c.scaling && !c.scaled_termination;
   auto products = [&](const double *vn, const double *vm, double *outA, double *outP, double *outT) {
     // outA = A vn (m), outP = P vn (n), outT = A' vm (n)
-    if (d.SA.paired) {
+    if (MODE(d.SA.paired, 1)) {
       stream_phase_paired(SG, d.SA, vn, [&](int r, double sum) {
         if (r < m) outA[r] = sum;
         else outP[r - m] = sum;
@@ -1601,7 +1613,7 @@ __device__ __noinline__ double wood_apply(Grid &g, RedSmem &sm, const DevPtrs &d
 __device__ __noinline__ void refresh_products_stream(Grid &g, Slice &SG, const DevPtrs &d, double sigma, int m0, int m1,
                                                      int n0, int n1) {
   const int tid = threadIdx.x, nth = blockDim.x, m = d.m;
-  if (d.SA.paired) {
+  if (MODE(d.SA.paired, 1)) {
     stream_phase_paired(SG, d.SA, d.xt, [&](int r, double sum) {
       if (r < m) {
         d.zt[r] = sum;
@@ -1658,8 +1670,8 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   }
   grid_barrier(g);
 
-  const bool wood = d.blocked && d.W.w > 0;
-  const bool slack = d.blocked && d.SL.rows > 0;
+  const bool wood = MODE(d.blocked && d.W.w > 0, false);
+  const bool slack = MODE(d.blocked && d.SL.rows > 0, false);
   if (wood && c.wood_refresh) wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
   if (slack && c.wood_refresh) slack_refresh(g, d, d.rho_vec, c.sigma, d.Minv, m0, m1, n0, n1);
 
@@ -1672,7 +1684,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   for (it = 1; it <= c.max_iter; it++) {
     // ---- P1: wv = rho .* z - y   (+ refresh: z_tilde = A x_tilde).  In steady state wv was already written by
     //         the Z phase of the previous iteration and its reduce + barrier made it visible: nothing to do here.
-    const bool refresh_on_streams = refresh && d.blocked && d.info_streams;
+    const bool refresh_on_streams = refresh && MODE(d.blocked, 1) && MODE(d.info_streams, 1);
     if (refresh || !wv_valid) {
     for (int i = m0 + tid; i < m1; i += nth) d.wv[i] = d.rho_vec[i] * d.z[i] - d.y[i];
     wv_valid = true;
@@ -1698,7 +1710,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
     }
     // ---- P2: b = sigma x - q + A' wv ; r = b - K x_tilde (refresh) or r += b - b_old
     double red3[3] = {0.0, 0.0, 0.0};
-    if (d.blocked && (!refresh || refresh_on_streams)) {
+    if (MODE(d.blocked, 1) && (!refresh || refresh_on_streams)) {
       // A' wv through the staged tiles, then the element-wise part on the owner block (a refresh rebuilds the
       // residual from K x_tilde in d.w, the steady state carries it by recurrence)
       if (d.m > 0) {
@@ -1776,7 +1788,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       const double tfl = c.pcg_floor * red3[2], ee2 = ee * ee;
       int ncg = slack     ? pcg_run_stream_slack(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[1],
                                                  thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
-                : d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                : MODE(d.blocked, 1) ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
                                            red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
                           : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
                                     thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2);
@@ -1820,7 +1832,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       d.dx[j] = xn - xj;
       d.x[j] = xn;
     }
-    if (d.blocked && d.m > 0) stream_prefetch_head(d.ST);
+    if (MODE(d.blocked, 1) && d.m > 0) stream_prefetch_head(d.ST);
     {
       double redt[1] = {0.0};
       if (b == 0 && tid == 0) redt[0] = (double)(globaltimer_ns() - t_start) * 1e-9;
@@ -1837,7 +1849,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
     can_check = c.check_termination && (it % c.check_termination == 0);
     can_print = c.verbose && ((it % kPrintInterval == 0) || it == 1);
     if (can_check || can_print) {
-      if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      if (MODE(d.blocked, 1) && MODE(d.info_streams, 1)) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       pc.tick(12);
       info_iter = it;
@@ -1860,7 +1872,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
     }
     if (c.adaptive_rho && interval && (it % interval == 0)) {
       if (!can_check && !can_print) {
-        if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+        if (MODE(d.blocked, 1) && MODE(d.info_streams, 1)) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
         info_iter = it;
         checks++;
@@ -1891,7 +1903,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   }
   if (!can_check) {
     if (!can_print) {
-      if (d.blocked && d.info_streams) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
+      if (MODE(d.blocked, 1) && MODE(d.info_streams, 1)) compute_info_stream(g, sm, SG, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       else compute_info(g, sm, d, c, cost_c, cost_cinv, d.x, d.z, d.y, m0, m1, n0, n1, S);
       info_iter = it - 1;
       checks++;
@@ -1961,6 +1973,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   }
 }
 
+#ifndef OSQP_B200_FAST  // (only the ADMM and polish kernels are compiled a second time)
 // ------------------------------------------------------------------ setup-time curvature probe
 // libosqp fails osqp_setup when the LDL' of the KKT matrix has a wrong-sign pivot, i.e. when
 // P + sigma I is not positive definite (test/non_convex.jl:13-21).  Without a factorisation we
@@ -2049,6 +2062,8 @@ __global__ void k_gershgorin(const DevPtrs d, double sigma) {
   }
 }
 
+#endif  // !OSQP_B200_FAST
+
 // ------------------------------------------------------------------ polish (row a12)
 // Active-set guess as in libosqp (z - l < -y lower-active, u - z < y upper-active), then the
 // equality-constrained QP  min 1/2 x'Px + q'x  s.t. A_act x = b_act  is solved by a proximal
@@ -2092,7 +2107,7 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
   const long long n_active = (long long)(cnt[0] + 0.5);
   // preconditioner for K_pol
   double *Minv_pol = d.pol_rhs;  // pol_rhs is free here
-  const bool wood = d.blocked && d.W.w > 0;
+  const bool wood = MODE(d.blocked && d.W.w > 0, false);
   if (wood) wood_refresh(g, sm, d, d.pol_rho, c.delta, Minv_pol, n0, n1);
   else precond_rows(d, d.pol_rho, c.delta, Minv_pol, n0, n1);
   long long cg_total = 0;
@@ -2148,7 +2163,7 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
     }
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
     {
-      const int ncg = d.blocked ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
+      const int ncg = MODE(d.blocked, 1) ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
                                                  red3[0], red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
                                 : pcg_run(g, sm, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1);
@@ -2211,6 +2226,7 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
   }
 }
 
+#ifndef OSQP_B200_FAST
 // ------------------------------------------------------------------ standalone SpMV (profiling / parity)
 // which: 0  out = A in (m) | 1  out = A' in (n) | 2  out = (P + sigma I) in (n)
 __global__ void __launch_bounds__(kThreads, 1) spmv_kernel(const DevPtrs d, int which, const double *in, double *out,
@@ -2268,7 +2284,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const __grid_c
   grid_barrier(g);
   if (tid == 0) probe[1] = globaltimer_ns();
   SG.probe = probe;
-  if (which != 1 && d.SA.paired) {
+  if (which != 1 && MODE(d.SA.paired, 1)) {
     stream_phase_paired(SG, d.SA, in, [&](int r, double sum) {
       if (which == 0 && r < d.m) out[r] = sum;
       if (which == 2 && r >= d.m) out[r - d.m] = sum + sigma * in[r - d.m];
@@ -2287,7 +2303,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const __grid_c
   if (tid == 0) probe[5] = globaltimer_ns();
   if (which == 1) {
     for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.ST, j);
-  } else if (!d.SA.paired) {
+  } else if (!MODE(d.SA.paired, 1)) {
     if (which == 0)
       for (int i = m0 + tid; i < m1; i += nth) out[i] = part_sum(d.SA, i);
     else
@@ -2640,6 +2656,8 @@ inline int ew_grid(long long work) {
   return (int)g;
 }
 
+#endif  // !OSQP_B200_FAST
+
 template <typename... Args>
 cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cudaStream_t st, Args... args) {
   cudaError_t e = cudaMemsetAsync(bar, 0, kBarBytes, st);  // grid barrier arrival counter + fixed-point accumulators
@@ -2667,7 +2685,29 @@ cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cu
 
 }  // namespace
 
+#ifdef OSQP_B200_FAST
+// ------------------------------------------------------------------ host wrappers of the fixed-mode kernels
+cudaError_t launch_solve_fast(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
+  return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
+}
+cudaError_t launch_polish_fast(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
+                               cudaStream_t st) {
+  return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
+}
+void fast_kernels(const void **admm, const void **polish) {
+  *admm = (const void *)admm_kernel;
+  *polish = (const void *)polish_kernel;
+}
+#else
 // ------------------------------------------------------------------ host wrappers
+// The mode the second compilation fixes (see the top of this file): tile streams in the lane-row layout, [A; P] in
+// cluster pairs, fp32 slices, update_info on the streams, plain Jacobi preconditioner.  Evaluated at every launch, so
+// a workspace that loses its cluster pairs (osqp_abi.cu launch_with_pair_fallback) moves to the plain kernels.
+bool fast_mode(const DevPtrs &d, const LaunchGeom &g) {
+  return g.fast && g.cluster == 2 && d.blocked && d.SA.paired && d.SA.lane_rows && (d.m == 0 || d.ST.lane_rows) &&
+         d.f32_slices && d.info_streams && d.W.w == 0 && d.SL.rows == 0;
+}
+
 cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma, cudaStream_t st) {
   const long long rows = (long long)d.n + d.m;
   const int gw = ew_grid(rows * 32), ge = ew_grid(d.A.nnz + d.P.nnz + rows);
@@ -2733,6 +2773,7 @@ cudaError_t launch_scatter_values(double *dst, const double *vals, const long lo
 }
 
 cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
+  if (fast_mode(d, g)) return launch_solve_fast(d, cfg, g, st);
   return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
 }
 
@@ -2814,7 +2855,13 @@ cudaError_t raise_dyn_smem(const void *func, size_t bytes) {
 }
 
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
-  cudaError_t e = raise_dyn_smem((const void *)admm_kernel, dyn_smem);
+  const void *fa = nullptr, *fp = nullptr;
+  fast_kernels(&fa, &fp);
+  cudaError_t e = raise_dyn_smem(fa, dyn_smem);
+  if (e != cudaSuccess) return e;
+  e = raise_dyn_smem(fp, dyn_smem);
+  if (e != cudaSuccess) return e;
+  e = raise_dyn_smem((const void *)admm_kernel, dyn_smem);
   if (e != cudaSuccess) return e;
   e = raise_dyn_smem((const void *)spmv_stream_kernel, dyn_smem);
   if (e != cudaSuccess) return e;
@@ -2824,20 +2871,30 @@ cudaError_t configure_dyn_smem(size_t dyn_smem) {
 int coop_threads() { return kThreads; }
 
 size_t coop_static_smem() {
-  cudaFuncAttributes a{}, b{};
-  if (cudaFuncGetAttributes(&a, admm_kernel) != cudaSuccess || cudaFuncGetAttributes(&b, polish_kernel) != cudaSuccess) {
-    cudaGetLastError();
-    return 16384;
+  const void *f[4] = {(const void *)admm_kernel, (const void *)polish_kernel, nullptr, nullptr};
+  fast_kernels(&f[2], &f[3]);
+  size_t most = 0;
+  for (const void *k : f) {
+    cudaFuncAttributes a{};
+    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) {
+      cudaGetLastError();
+      return 16384;
+    }
+    most = a.sharedSizeBytes > most ? a.sharedSizeBytes : most;
   }
-  return a.sharedSizeBytes > b.sharedSizeBytes ? a.sharedSizeBytes : b.sharedSizeBytes;
+  return most;
 }
 
 int max_coop_blocks_per_sm(int block, size_t dyn_smem) {
-  int nb = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, admm_kernel, block, dyn_smem) != cudaSuccess) return 0;
-  int nb2 = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, polish_kernel, block, dyn_smem) != cudaSuccess) return 0;
-  return nb < nb2 ? nb : nb2;
+  const void *f[4] = {(const void *)admm_kernel, (const void *)polish_kernel, nullptr, nullptr};
+  fast_kernels(&f[2], &f[3]);
+  int least = 1 << 30;
+  for (const void *k : f) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, block, dyn_smem) != cudaSuccess) return 0;
+    least = nb < least ? nb : least;
+  }
+  return least;
 }
 
 cudaError_t launch_fill_blocked(const DevPtrs &d, cudaStream_t st) {
@@ -2852,7 +2909,9 @@ cudaError_t launch_fill_wood(const DevPtrs &d, cudaStream_t st) {
 
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                           cudaStream_t st) {
+  if (fast_mode(d, g)) return launch_polish_fast(d, cfg, sc, out, g, st);
   return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
 }
+#endif  // OSQP_B200_FAST
 
 }  // namespace osqpb200

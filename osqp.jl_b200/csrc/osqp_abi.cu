@@ -1418,6 +1418,7 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
         ok = (long long)e.geom.dyn_smem <= smem_budget;  // pairs need room for the row accumulators: else retry without
       }
       e.geom.cluster = (ok && hA.paired) ? 2 : 1;
+      e.geom.fast = env_int("OSQP_B200_FAST_KERNELS", 1) != 0;
       if (env_int("OSQP_B200_DEBUG", 0))
         fprintf(stderr, "[osqp_b200] tile streams ok=%d paired=%d groups=%d/%d slice=%d rows=%d dyn_smem=%zu budget=%lld\n",
                 (int)ok, hA.paired, hA.ngroups, hT.ngroups, d.smem_x_elems, d.smem_rows, e.geom.dyn_smem, smem_budget);
@@ -1648,6 +1649,7 @@ static c_int solve_impl(Engine &e) {
 
   CU_OK(cudaEventRecord(e.ev0, e.stream));
   CU_OK(launch_with_pair_fallback(e, [&]() { return launch_solve(e.d, c, e.geom, e.stream); }));
+  e.prof.fast_kernels = fast_mode(e.d, e.geom) ? 1 : 0;
   CU_OK(cudaEventRecord(e.ev1, e.stream));
   e.prof.launches += 1;
   e.wood_dirty = false;  // the launch leaves the Woodbury data consistent with the rho it ends on

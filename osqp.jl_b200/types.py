@@ -175,4 +175,4 @@ class B200Profile(C.Structure):
                                      "admm_iters", "pcg_iters", "info_evals", "refreshes")] + \
                [(k, c_float) for k in ("kernel_ms", "polish_ms", "alg_bytes", "spmv_bytes_A", "spmv_bytes_At",
                                        "spmv_bytes_P")] + [("phase_us", c_float * 16)] + \
-               [(k, c_int) for k in ("streams", "groups_A", "groups_At", "paired")]
+               [(k, c_int) for k in ("streams", "groups_A", "groups_At", "paired", "fast_kernels")]

@@ -444,6 +444,42 @@ def test_two_models_with_different_slices_coexist(pkg, engine_lib):
     m2.clean()
 
 
+def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
+    # csrc/kernels_fast.cu: the ADMM and polish kernels compiled with the storage mode of the common large sparse
+    # problem fixed (lane rows, cluster pairs, fp32 slices, Jacobi).  Same source, same arithmetic: the two
+    # compilations must take the same iterations to the same point; a workspace that is not in that mode (here: one
+    # with the Woodbury preconditioner switched on by an equality row) must stay on the plain kernels.
+    eng = pkg.load_library(engine_lib)
+    prob = random_qp(40000, 60000, 0.0008, 71)
+    opts = dict(FIXED_RHO, eps_abs=1e-4, eps_rel=1e-4, check_termination=25, polish=True)
+    out = {}
+    for fast in (1, 0):
+        monkeypatch.setenv("OSQP_B200_FAST_KERNELS", str(fast))
+        mdl = pkg.Model(lib=engine_lib)
+        mdl.setup(**prob, **opts)
+        r = mdl.solve()
+        prof = pkg.types.B200Profile()
+        assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
+        assert (int(prof.streams), int(prof.paired), int(prof.fast_kernels)) == (1, 1, fast)
+        out[fast] = r
+        mdl.clean()
+    a, b = out[1], out[0]
+    assert a.info.status == b.info.status == "Solved" and a.info.iter == b.info.iter
+    assert a.info.status_polish == b.info.status_polish
+    assert np.max(np.abs(a.x - b.x)) <= 1e-9 * (1 + np.max(np.abs(b.x)))
+    assert np.max(np.abs(a.y - b.y)) <= 1e-9 * (1 + np.max(np.abs(b.y)))
+    monkeypatch.setenv("OSQP_B200_FAST_KERNELS", "1")
+    eq = dict(prob)
+    eq["l"] = prob["l"].copy()
+    eq["l"][:4] = prob["u"][:4]  # a few equality rows -> Woodbury members
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**eq, **dict(opts, polish=False))
+    r = mdl.solve()
+    assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
+    assert r.info.status == "Solved" and int(prof.streams) == 1 and int(prof.fast_kernels) == 0
+    mdl.clean()
+
+
 def test_tiny_mode_settings_variants_match_oracle(pkg, engine_lib, oracle_lib):
     # n, m <= 256: the workspace also lives in the batched engine and is solved there; the settings
     # that change the arithmetic must reach it
