@@ -59,6 +59,7 @@ struct TileStreamDev {
   int pf_chunks = 0;             // chunks (32 quads = 1280 B) a warp prefetches into L2 ahead of its register loads
   long long nelem = 0;           // padded stream length in entries (multiple of 4)
   double *val = nullptr;         // [nelem] scaled values (zero on padding)
+  float *val32 = nullptr;        // [nelem] the same values rounded to fp32, in entry order (DevPtrs::mat32), or nullptr
   unsigned short *cf = nullptr;  // [nelem] local column; bit 15 of every 4th word: row ends with this quad
   int *from_csr = nullptr;       // stacked CSR position -> stream position (value refresh after re-scaling)
   int *blk_group = nullptr;      // [grid]
@@ -187,6 +188,12 @@ struct DevPtrs {
   int blocked = 0;
   int info_streams = 0;          // 1: update_info and the residual refresh also run on the tile streams
   TileStreamDev SA, ST;          // [A; P] against an n-vector, A' against an m-vector
+  // mat32 == 1: the PCG phases of the fixed-mode kernels (kernels_fast.cu) stream SA.val32 / ST.val32 instead of the
+  // fp64 values: 6 instead of 10 bytes per entry, so that both streams of a PCG iteration stay resident in L2.  The
+  // PCG then iterates on K~ = K(1 + 6e-8): every right-hand side, the z~ = A x~ and residual rebuilds of a refresh and
+  // update_info stay on the fp64 values, so the recurrences r += b - b_old, z~ += alpha A p only ever carry
+  // (K - K~)(x~ - x~ at the last refresh), which vanishes as the iterates converge.
+  int mat32 = 0;
   // fp32 shadows of the two vectors the PCG phases gather (u = M^{-1} r and rho .* (A u)): the staged slices of
   // these phases are fp32 (half the L2 -> SM traffic of the staging); u is rounded BEFORE it enters the recurrences, so
   // CG stays exact for a preconditioner perturbed at the 6e-8 level; the rounding of rho .* (A u) perturbs one K-apply

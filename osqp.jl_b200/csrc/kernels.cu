@@ -19,6 +19,7 @@
 
 #include <map>
 #include <mutex>
+#include <type_traits>
 #include <utility>
 
 // This file is compiled TWICE.  The plain compilation holds every kernel and decides the storage mode of a workspace
@@ -190,13 +191,31 @@ __device__ __forceinline__ void quad_load(QuadSlot &q, const char *pv, const cha
   }
 }
 
+// The same for the fp32 copy of the values (TileStreamDev::val32, entry order): one 16 B load per lane and chunk.
+struct QuadSlot32 {
+  float v0, v1, v2, v3;
+  unsigned c01, c23;
+};
+__device__ __forceinline__ void quad_load(QuadSlot32 &q, const char *pv, const char *pc, bool active) {
+  q.v0 = q.v1 = q.v2 = q.v3 = 0.f;
+  q.c01 = q.c23 = 0u;
+  if (active) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(q.v0), "=f"(q.v1), "=f"(q.v2), "=f"(q.v3)
+                 : "l"(pv));
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(q.c01), "=r"(q.c23) : "l"(pc));
+  }
+}
+
 // Warm L2 with the head of this warp's stream of T; call before the grid barrier that precedes the phase.
+template <bool kM32 = false>
 __device__ __forceinline__ void stream_prefetch_head(const TileStreamDev &T) {
   const int lane = threadIdx.x & 31, wid = blockIdx.x * kWarps + (threadIdx.x >> 5);
   const int q0 = __ldg(T.w_q0 + wid), total = __ldg(T.w_qn + wid);
   if (lane < T.pf_chunks && lane * 32 < total) {
     const unsigned quads = (unsigned)min(32, total - lane * 32);
-    l2_prefetch(T.val + 4ll * (q0 + lane * 32), 1024u);
+    if (kM32) l2_prefetch(T.val32 + 4ll * (q0 + lane * 32), 512u);
+    else l2_prefetch(T.val + 4ll * (q0 + lane * 32), 1024u);
     l2_prefetch(T.cf + 4ll * (q0 + lane * 32), quads * 8u);
   }
 }
@@ -379,9 +398,16 @@ __device__ __noinline__ void stream_phase_impl(Slice &S, const TileStreamDev &T,
 #define OSQP_B200_DEPTH_LR 4
 #endif
 constexpr int kDepthLR = OSQP_B200_DEPTH_LR;
+#ifndef OSQP_B200_DEPTH_LR32
+#define OSQP_B200_DEPTH_LR32 4
+#endif
+constexpr int kDepthLR32 = OSQP_B200_DEPTH_LR32;  // chunks in flight per lane on the fp32 value streams (6 registers a slot)
 
-template <int kD, bool kPair, bool kF32>
+// kM32: the values come from the fp32 copy T.val32 (engine.cuh DevPtrs::mat32): 6 instead of 10 bytes per entry.
+template <int kD, bool kPair, bool kF32, bool kM32 = false>
 __device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, const void *__restrict__ vec) {
+  using Slot = typename std::conditional<kM32, QuadSlot32, QuadSlot>::type;
+  constexpr int kValBytes = kM32 ? 512 : 1024;  // value bytes of a chunk
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x;
   const int grp = __ldg(T.blk_group + b);
   const unsigned parity = S.parity;
@@ -413,30 +439,31 @@ __device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, c
   int left = __ldg(T.sl_len + sl), myrow = __ldg(T.sl_row + (size_t)sl * 32 + lane);
   int nleft = 0, nrow = -1;
   if (sl + 1 < sl_end) { nleft = __ldg(T.sl_len + sl + 1); nrow = __ldg(T.sl_row + (size_t)(sl + 1) * 32 + lane); }
-  const char *pv = reinterpret_cast<const char *>(T.val) + 32ll * q0 + 16 * lane;
+  const char *vbase = kM32 ? reinterpret_cast<const char *>(T.val32) : reinterpret_cast<const char *>(T.val);
+  const char *pv = vbase + (kM32 ? 16ll : 32ll) * q0 + 16 * lane;
   const char *pc = reinterpret_cast<const char *>(T.cf) + 8ll * (q0 + lane);
-  const char *pf_v = reinterpret_cast<const char *>(T.val) + 32ll * q0;
+  const char *pf_v = vbase + (kM32 ? 16ll : 32ll) * q0;
   const char *pf_c = reinterpret_cast<const char *>(T.cf) + 8ll * q0;
   const int pf = T.pf_chunks;
   const unsigned xs = S.xs;
   int issued = 0;
   double acc = 0.0;
 
-  auto issue = [&](QuadSlot &q) {
+  auto issue = [&](Slot &q) {
     quad_load(q, pv, pc, issued < nchunks);
-    pv += 1024;
+    pv += kValBytes;
     pc += 256;
     if ((issued & 3) == 0 && lane == 0 && pf > 0) {  // every 4th chunk: the 4 chunks `pf` ahead go to L2
       const int pq = issued + pf;
       if (pq < nchunks) {
         const unsigned ch = (unsigned)min(4, nchunks - pq);
-        l2_prefetch(pf_v + 1024ll * pq, ch * 1024u);
+        l2_prefetch(pf_v + (long long)kValBytes * pq, ch * (unsigned)kValBytes);
         l2_prefetch(pf_c + 256ll * pq, ch * 256u);
       }
     }
     issued++;
   };
-  auto consume = [&](const QuadSlot &q) {
+  auto consume = [&](const Slot &q) {
     double x0, x1, x2, x3;
     if (kF32) {
       x0 = (double)lds_f32(xs + ((q.c01 & 0x7fffu) << 2)); x1 = (double)lds_f32(xs + ((q.c01 >> 14) & 0x1fffcu));
@@ -445,10 +472,10 @@ __device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, c
       x0 = lds_f64(xs + ((q.c01 & 0x7fffu) << 3)); x1 = lds_f64(xs + ((q.c01 >> 13) & 0x3fff8u));
       x2 = lds_f64(xs + ((q.c23 & 0x7fffu) << 3)); x3 = lds_f64(xs + ((q.c23 >> 13) & 0x3fff8u));
     }
-    double inc = q.v0 * x0;
-    inc = fma(q.v1, x1, inc);
-    inc = fma(q.v2, x2, inc);
-    inc = fma(q.v3, x3, inc);
+    double inc = (double)q.v0 * x0;  // (fp32 values and fp32 slice entries: the products are exact in fp64)
+    inc = fma((double)q.v1, x1, inc);
+    inc = fma((double)q.v2, x2, inc);
+    inc = fma((double)q.v3, x3, inc);
     acc += inc;
     if (--left == 0) {  // warp-uniform: the slice ends with this chunk
       if (myrow >= 0) {
@@ -463,7 +490,7 @@ __device__ __noinline__ void stream_phase_lr(Slice &S, const TileStreamDev &T, c
     }
   };
 
-  QuadSlot slot[kD];
+  Slot slot[kD];
 #pragma unroll
   for (int k = 0; k < kD; k++) issue(slot[k]);
   mbar_wait(S.mbar, parity);  // the slice has landed (the first matrix loads are already in flight)
@@ -481,8 +508,9 @@ __device__ __forceinline__ void stream_phase(Slice &S, const TileStreamDev &T, c
   if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, false, false>(S, T, vec);
   else stream_phase_impl<kDepth, false, false>(S, T, vec);
 }
+template <bool kM32 = false>
 __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &T, const float *__restrict__ vec) {
-  if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, false, true>(S, T, vec);
+  if (MODE(T.lane_rows, 1)) stream_phase_lr<kM32 ? kDepthLR32 : kDepthLR, false, true, kM32>(S, T, vec);
   else stream_phase_impl<kDepth, false, true>(S, T, vec);
 }
 
@@ -491,10 +519,10 @@ __device__ __forceinline__ void stream_phase_f32(Slice &S, const TileStreamDev &
 // reading its partner's partial sums through distributed shared memory, and hands the complete row sum to
 // fin(stacked_row, sum).  No partial vector goes through global memory and no grid barrier is needed for the combine.
 // Every thread of both blocks must call this; the accumulators are next written after at least one grid barrier.
-template <bool kF32 = false, typename Fin>
+template <bool kF32 = false, bool kM32 = false, typename Fin>
 __device__ __forceinline__ void stream_phase_paired(Slice &S, const TileStreamDev &T, const void *__restrict__ vec,
                                                     Fin fin) {
-  if (MODE(T.lane_rows, 1)) stream_phase_lr<kDepthLR, true, kF32>(S, T, vec);
+  if (MODE(T.lane_rows, 1)) stream_phase_lr<kM32 ? kDepthLR32 : kDepthLR, true, kF32, kM32>(S, T, vec);
   else stream_phase_impl<kDepth, true, kF32>(S, T, vec);
   cluster_sync();
   const int b = blockIdx.x, r0 = __ldg(T.blk_row0 + b), r1 = __ldg(T.blk_row1 + b);
@@ -915,6 +943,8 @@ __device__ __forceinline__ double part_sum(const TileStreamDev &T, int row) {
 //   phase C : owners: t = sum of partials, tr = rho .* t, Pu; delta = uu'P uu + sigma |uu|^2 + t'tr | reduce + barrier
 //   phase B : A' tr      -> partial row sums per column group                      | barrier
 //   phase V : owners: w = Pu + sigma uu + sum of partials, vector recurrences      | reduce + barrier
+// kM32: the two stream phases read the fp32 copies of the matrix values (engine.cuh DevPtrs::mat32).
+template <bool kM32>
 __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, PhaseClock &pc, const DevPtrs &d,
                                            const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma, double *xvec,
                                            double *zvec, double gamma, double rn, double thresh, int max_it, int m0,
@@ -948,15 +978,15 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
           red1[0] += uj * (sum + sigma * uj);
         }
       };
-      if (MODE(d.f32_slices, 1)) stream_phase_paired<true>(S, d.SA, d.uu32, fin);
+      if (MODE(d.f32_slices, 1)) stream_phase_paired<true, kM32>(S, d.SA, d.uu32, fin);
       else stream_phase_paired<false>(S, d.SA, v.uu, fin);
-      if (m > 0) stream_prefetch_head(d.ST);
+      if (m > 0) stream_prefetch_head<kM32>(d.ST);
       pc.tick(0);
     } else {
     // ---- phase A
     if (MODE(d.f32_slices, 1)) stream_phase_f32(S, d.SA, d.uu32);
     else stream_phase(S, d.SA, v.uu);
-    if (m > 0) stream_prefetch_head(d.ST);
+    if (m > 0) stream_prefetch_head<kM32>(d.ST);
     pc.tick(0);
     grid_barrier(g);
     pc.tick(1);
@@ -995,9 +1025,9 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       reduce_and_barrier_fx<1>(g, sm, red1, 0u, gamma);  // delta / gamma is a Rayleigh quotient of M^-1 K
       pc.tick(3);
       // ---- phase B
-      if (MODE(d.f32_slices, 1)) stream_phase_f32(S, d.ST, d.tr32);
+      if (MODE(d.f32_slices, 1)) stream_phase_f32<kM32>(S, d.ST, d.tr32);
       else stream_phase(S, d.ST, v.tr);
-      stream_prefetch_head(d.SA);
+      stream_prefetch_head<kM32>(d.SA);
       pc.tick(4);
       grid_barrier(g);
       pc.tick(5);
@@ -1715,7 +1745,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       // residual from K x_tilde in d.w, the steady state carries it by recurrence)
       if (d.m > 0) {
         stream_phase(SG, d.ST, d.wv);
-        stream_prefetch_head(d.SA);
+        stream_prefetch_head<MODE(false, true)>(d.SA);
         grid_barrier(g);
         pc.tick(9);
       }
@@ -1788,7 +1818,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       const double tfl = c.pcg_floor * red3[2], ee2 = ee * ee;
       int ncg = slack     ? pcg_run_stream_slack(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[1],
                                                  thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
-                : MODE(d.blocked, 1) ? pcg_run_stream(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
+                : MODE(d.blocked, 1) ? pcg_run_stream<MODE(false, true)>(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
                                            red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
                           : pcg_run(g, sm, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0], red3[1],
                                     thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2);
@@ -2163,7 +2193,7 @@ __global__ void __launch_bounds__(kThreads, 1) polish_kernel(const __grid_consta
     }
     const double thresh = c.pcg_rel_tol * fmax(red3[2], 1e-3);
     {
-      const int ncg = MODE(d.blocked, 1) ? pcg_run_stream(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
+      const int ncg = MODE(d.blocked, 1) ? pcg_run_stream<false>(g, sm, SG, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z,
                                                  red3[0], red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1)
                                 : pcg_run(g, sm, pc, d, pv, d.pol_rho, Minv_pol, c.delta, d.pol_x, d.pol_z, red3[0],
                                           red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1);
@@ -2632,11 +2662,24 @@ __global__ void k_scatter(double *dst, const double *vals, const long long *idx,
 // tile streams <- scaled CSR values (padding entries stay zero)
 __global__ void k_fill_blocked(const DevPtrs d) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+  // (val is chunk-interleaved, osqp_abi.cu stream_val_pos; val32 is in entry order: invert the interleave)
+  auto entry_of = [](int vp) { return (vp & ~127) + (((vp & 63) >> 1) << 2) + (((vp >> 6) & 1) << 1) + (vp & 1); };
   for (long long k = tid; k < d.A.nnz; k += nth) {
-    d.SA.val[d.SA.from_csr[k]] = d.A.val[k];
-    d.ST.val[d.ST.from_csr[k]] = d.At.val[k];
+    const int pa = d.SA.from_csr[k], pt = d.ST.from_csr[k];
+    const double a = d.A.val[k], t = d.At.val[k];
+    d.SA.val[pa] = a;
+    d.ST.val[pt] = t;
+    if (d.mat32) {
+      d.SA.val32[entry_of(pa)] = (float)a;
+      d.ST.val32[entry_of(pt)] = (float)t;
+    }
   }
-  for (long long k = tid; k < d.P.nnz; k += nth) d.SA.val[d.SA.from_csr[d.A.nnz + k]] = d.P.val[k];
+  for (long long k = tid; k < d.P.nnz; k += nth) {
+    const int pp = d.SA.from_csr[d.A.nnz + k];
+    const double v = d.P.val[k];
+    d.SA.val[pp] = v;
+    if (d.mat32) d.SA.val32[entry_of(pp)] = (float)v;
+  }
 }
 
 // compact copies of the Woodbury member rows <- scaled CSR values of A
@@ -2701,11 +2744,12 @@ void fast_kernels(const void **admm, const void **polish) {
 #else
 // ------------------------------------------------------------------ host wrappers
 // The mode the second compilation fixes (see the top of this file): tile streams in the lane-row layout, [A; P] in
-// cluster pairs, fp32 slices, update_info on the streams, plain Jacobi preconditioner.  Evaluated at every launch, so
+// cluster pairs, fp32 slices and fp32 copies of the matrix values in the PCG phases (DevPtrs::mat32), update_info on
+// the streams, plain Jacobi preconditioner.  Evaluated at every launch, so
 // a workspace that loses its cluster pairs (osqp_abi.cu launch_with_pair_fallback) moves to the plain kernels.
 bool fast_mode(const DevPtrs &d, const LaunchGeom &g) {
   return g.fast && g.cluster == 2 && d.blocked && d.SA.paired && d.SA.lane_rows && (d.m == 0 || d.ST.lane_rows) &&
-         d.f32_slices && d.info_streams && d.W.w == 0 && d.SL.rows == 0;
+         d.f32_slices && d.info_streams && d.W.w == 0 && d.SL.rows == 0 && d.mat32;
 }
 
 cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma, cudaStream_t st) {

@@ -1525,6 +1525,18 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
     }
   }
 
+  // fp32 copies of the stream values for the PCG phases of the fixed-mode kernels (engine.cuh DevPtrs::mat32)
+  d.mat32 = 0;
+  if (env_int("OSQP_B200_MAT32", 1) != 0) {
+    d.mat32 = 1;  // provisional: fast_mode() looks at it
+    if (fast_mode(d, e.geom)) {
+      CU_OK(dalloc(e, &d.SA.val32, (size_t)d.SA.nelem + 8));
+      if (m > 0) CU_OK(dalloc(e, &d.ST.val32, (size_t)d.ST.nelem + 8));
+    } else {
+      d.mat32 = 0;
+    }
+  }
+
   mark("tile streams (host build + upload)");
   // ---- state, scaling (a2), rho vector (a3), preconditioner, convexity probe
   e.st.rho = std::min(std::max(e.st.rho, kRhoMin), kRhoMax);

@@ -17,6 +17,8 @@ VARIANTS = {
     "lr6": dict(OSQP_B200_DEPTH_LR=6),
     "lr8": dict(OSQP_B200_DEPTH_LR=8),
     "lr2": dict(OSQP_B200_DEPTH_LR=2),
+    "m32d6": dict(OSQP_B200_DEPTH_LR32=6),
+    "m32d8": dict(OSQP_B200_DEPTH_LR32=8),
 }
 
 if __name__ == "__main__":

@@ -446,9 +446,10 @@ def test_two_models_with_different_slices_coexist(pkg, engine_lib):
 
 def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
     # csrc/kernels_fast.cu: the ADMM and polish kernels compiled with the storage mode of the common large sparse
-    # problem fixed (lane rows, cluster pairs, fp32 slices, Jacobi).  Same source, same arithmetic: the two
-    # compilations must take the same iterations to the same point; a workspace that is not in that mode (here: one
-    # with the Woodbury preconditioner switched on by an equality row) must stay on the plain kernels.
+    # problem fixed (lane rows, cluster pairs, fp32 slices, Jacobi); its PCG phases stream fp32 copies of the matrix
+    # values (DevPtrs::mat32), everything else is the same source.  Both compilations must end at the same termination
+    # check with the same polished point; a workspace that is not in that mode (here: one with the Woodbury
+    # preconditioner switched on by an equality row) must stay on the plain kernels.
     eng = pkg.load_library(engine_lib)
     prob = random_qp(40000, 60000, 0.0008, 71)
     opts = dict(FIXED_RHO, eps_abs=1e-4, eps_rel=1e-4, check_termination=25, polish=True)
@@ -464,10 +465,11 @@ def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
         out[fast] = r
         mdl.clean()
     a, b = out[1], out[0]
-    assert a.info.status == b.info.status == "Solved" and a.info.iter == b.info.iter
+    assert a.info.status == b.info.status == "Solved" and abs(a.info.iter - b.info.iter) <= 25
     assert a.info.status_polish == b.info.status_polish
-    assert np.max(np.abs(a.x - b.x)) <= 1e-9 * (1 + np.max(np.abs(b.x)))
-    assert np.max(np.abs(a.y - b.y)) <= 1e-9 * (1 + np.max(np.abs(b.y)))
+    tol = 1e-7 if a.info.status_polish == 1 else 10 * opts["eps_abs"]  # unpolished: two points inside the tolerance
+    assert np.max(np.abs(a.x - b.x)) <= tol * (1 + np.max(np.abs(b.x)))
+    assert np.max(np.abs(a.y - b.y)) <= tol * (1 + np.max(np.abs(b.y)))
     monkeypatch.setenv("OSQP_B200_FAST_KERNELS", "1")
     eq = dict(prob)
     eq["l"] = prob["l"].copy()
