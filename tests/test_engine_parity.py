@@ -470,6 +470,20 @@ def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
     tol = 1e-7 if a.info.status_polish == 1 else 10 * opts["eps_abs"]  # unpolished: two points inside the tolerance
     assert np.max(np.abs(a.x - b.x)) <= tol * (1 + np.max(np.abs(b.x)))
     assert np.max(np.abs(a.y - b.y)) <= tol * (1 + np.max(np.abs(b.y)))
+    # tight tolerance: the PCG of the fixed-mode kernels iterates on fp32 copies of the matrix values, the right-hand
+    # sides and the periodic residual rebuilds use the fp64 values -- the difference must not leave an error floor
+    tight = dict(FIXED_RHO, eps_abs=1e-9, eps_rel=1e-9, check_termination=25, max_iter=40000)
+    res = {}
+    for fast in (1, 0):
+        monkeypatch.setenv("OSQP_B200_FAST_KERNELS", str(fast))
+        mdl = pkg.Model(lib=engine_lib)
+        mdl.setup(**prob, **tight)
+        res[fast] = mdl.solve()
+        mdl.clean()
+    assert res[1].info.status == res[0].info.status == "Solved"
+    assert abs(res[1].info.iter - res[0].info.iter) <= 25
+    assert np.max(np.abs(res[1].x - res[0].x)) <= 1e-8 * (1 + np.max(np.abs(res[0].x)))
+    assert np.max(np.abs(res[1].y - res[0].y)) <= 1e-8 * (1 + np.max(np.abs(res[0].y)))
     monkeypatch.setenv("OSQP_B200_FAST_KERNELS", "1")
     eq = dict(prob)
     eq["l"] = prob["l"].copy()
