@@ -41,7 +41,7 @@ typedef struct {
   c_int   groups_A;      /* column groups of the [A; P] stream and of the A' stream */
   c_int   groups_At;
   c_int   paired;        /* 1: [A; P] stream runs as cluster pairs with the DSMEM combine */
-  c_int   fast_kernels;  /* last solve: 1 = ran on the fixed-mode compilation of the kernels (csrc/kernels_fast.cu) */
+  c_int   fast_kernels;  /* last solve: 1 / 2 = ran on a fixed-mode compilation of the kernels (csrc/kernels_fast.cu, _fast2.cu) */
 } OSQPB200Profile;
 
 /* Measurement of the last osqp_solve on this workspace. */

@@ -258,7 +258,7 @@ struct LaunchGeom {
   int grid = 1, block = 1024;
   size_t dyn_smem = 0;
   int cluster = 1;  // thread blocks per cluster of the cooperative launches (2: TileStreamDev::paired)
-  int fast = 1;     // 0: never use the fixed-mode compilation of the ADMM / polish kernels (OSQP_B200_FAST_KERNELS=0)
+  int fast = 1;     // 0: never use the fixed-mode compilations of the ADMM / polish kernels (OSQP_B200_FAST_KERNELS=0)
 };
 
 // ---- host wrappers implemented in kernels.cu (all asynchronous on `st`)
@@ -274,12 +274,16 @@ cudaError_t launch_cold_start(const DevPtrs &d, cudaStream_t st);
 cudaError_t launch_scatter_values(double *dst, const double *vals, const long long *idx, const int *map,
                                   long long k, cudaStream_t st);
 cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
-// kernels_fast.cu: admm_kernel / polish_kernel compiled with the storage mode fixed (kernels.cu fast_mode)
-bool fast_mode(const DevPtrs &d, const LaunchGeom &g);
+// kernels_fast.cu / kernels_fast2.cu: admm_kernel / polish_kernel compiled with the storage mode fixed (kernels.cu fast_mode)
+int fast_mode(const DevPtrs &d, const LaunchGeom &g);
 cudaError_t launch_solve_fast(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
 cudaError_t launch_polish_fast(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                                cudaStream_t st);
-void fast_kernels(const void **admm, const void **polish);
+void kernels_fast(const void **admm, const void **polish);
+cudaError_t launch_solve_fast2(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
+cudaError_t launch_polish_fast2(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
+                                cudaStream_t st);
+void kernels_fast2(const void **admm, const void **polish);
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                           cudaStream_t st);
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,

@@ -30,8 +30,10 @@
 // (profiles/r2_ncu_admm.md section 5).  MODE(x, v) is x in the plain compilation and the constant v in the fast one.
 #ifdef OSQP_B200_FAST
 #define MODE(x, v) (v)
+#define FAST_PAIRED (OSQP_B200_FAST == 1)  // fixed mode 1: [A; P] in cluster pairs; fixed mode 2 (kernels_fast2.cu): no pairs
 #else
 #define MODE(x, v) (x)
+#define FAST_PAIRED 0
 #endif
 
 namespace osqpb200 {
@@ -964,7 +966,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
     // beta only needs the gammas of the previous reductions
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     double red1[1] = {0.0};
-    if (MODE(d.SA.paired, 1)) {
+    if (MODE(d.SA.paired, FAST_PAIRED)) {
       // ---- phase A with the combine fused in (cluster pairs): no partials, no extra grid barrier
       const bool rec = zvec != nullptr && it > 0;
       auto fin = [&](int r, double sum) {
@@ -984,7 +986,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
       pc.tick(0);
     } else {
     // ---- phase A
-    if (MODE(d.f32_slices, 1)) stream_phase_f32(S, d.SA, d.uu32);
+    if (MODE(d.f32_slices, 1)) stream_phase_f32<kM32>(S, d.SA, d.uu32);
     else stream_phase(S, d.SA, v.uu);
     if (m > 0) stream_prefetch_head<kM32>(d.ST);
     pc.tick(0);
@@ -1182,7 +1184,7 @@ __device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S,
     grid_barrier(g);
     pc.tick(7);
     // ---- A
-    if (MODE(d.SA.paired, 1)) {
+    if (MODE(d.SA.paired, FAST_PAIRED)) {
       auto fin = [&](int r, double sum) { finish(r, sum, red[0], red[1]); };
       stream_phase_paired<true>(S, d.SA, d.uu32, fin);
       pc.tick(0);
@@ -1354,7 +1356,7 @@ __device__ __noinline__ void compute_info_stream(Grid &g, RedSmem &sm, Slice &SG
   const bool unscale = c.scaling && !c.scaled_termination;
   auto products = [&](const double *vn, const double *vm, double *outA, double *outP, double *outT) {
     // outA = A vn (m), outP = P vn (n), outT = A' vm (n)
-    if (MODE(d.SA.paired, 1)) {
+    if (MODE(d.SA.paired, FAST_PAIRED)) {
       stream_phase_paired(SG, d.SA, vn, [&](int r, double sum) {
         if (r < m) outA[r] = sum;
         else outP[r - m] = sum;
@@ -1643,7 +1645,7 @@ __device__ __noinline__ double wood_apply(Grid &g, RedSmem &sm, const DevPtrs &d
 __device__ __noinline__ void refresh_products_stream(Grid &g, Slice &SG, const DevPtrs &d, double sigma, int m0, int m1,
                                                      int n0, int n1) {
   const int tid = threadIdx.x, nth = blockDim.x, m = d.m;
-  if (MODE(d.SA.paired, 1)) {
+  if (MODE(d.SA.paired, FAST_PAIRED)) {
     stream_phase_paired(SG, d.SA, d.xt, [&](int r, double sum) {
       if (r < m) {
         d.zt[r] = sum;
@@ -2314,7 +2316,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const __grid_c
   grid_barrier(g);
   if (tid == 0) probe[1] = globaltimer_ns();
   SG.probe = probe;
-  if (which != 1 && MODE(d.SA.paired, 1)) {
+  if (which != 1 && MODE(d.SA.paired, FAST_PAIRED)) {
     stream_phase_paired(SG, d.SA, in, [&](int r, double sum) {
       if (which == 0 && r < d.m) out[r] = sum;
       if (which == 2 && r >= d.m) out[r - d.m] = sum + sigma * in[r - d.m];
@@ -2333,7 +2335,7 @@ __global__ void __launch_bounds__(kThreads, 1) spmv_stream_kernel(const __grid_c
   if (tid == 0) probe[5] = globaltimer_ns();
   if (which == 1) {
     for (int j = n0 + tid; j < n1; j += nth) out[j] = part_sum(d.ST, j);
-  } else if (!MODE(d.SA.paired, 1)) {
+  } else if (!MODE(d.SA.paired, FAST_PAIRED)) {
     if (which == 0)
       for (int i = m0 + tid; i < m1; i += nth) out[i] = part_sum(d.SA, i);
     else
@@ -2730,26 +2732,44 @@ cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cu
 
 #ifdef OSQP_B200_FAST
 // ------------------------------------------------------------------ host wrappers of the fixed-mode kernels
-cudaError_t launch_solve_fast(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
+#if OSQP_B200_FAST == 1
+#define FASTNAME(x) x##_fast
+#else
+#define FASTNAME(x) x##_fast2
+#endif
+cudaError_t FASTNAME(launch_solve)(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
   return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
 }
-cudaError_t launch_polish_fast(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
-                               cudaStream_t st) {
+cudaError_t FASTNAME(launch_polish)(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
+                                    cudaStream_t st) {
   return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
 }
-void fast_kernels(const void **admm, const void **polish) {
+void FASTNAME(kernels)(const void **admm, const void **polish) {
   *admm = (const void *)admm_kernel;
   *polish = (const void *)polish_kernel;
 }
 #else
 // ------------------------------------------------------------------ host wrappers
-// The mode the second compilation fixes (see the top of this file): tile streams in the lane-row layout, [A; P] in
-// cluster pairs, fp32 slices and fp32 copies of the matrix values in the PCG phases (DevPtrs::mat32), update_info on
-// the streams, plain Jacobi preconditioner.  Evaluated at every launch, so
-// a workspace that loses its cluster pairs (osqp_abi.cu launch_with_pair_fallback) moves to the plain kernels.
-bool fast_mode(const DevPtrs &d, const LaunchGeom &g) {
-  return g.fast && g.cluster == 2 && d.blocked && d.SA.paired && d.SA.lane_rows && (d.m == 0 || d.ST.lane_rows) &&
-         d.f32_slices && d.info_streams && d.W.w == 0 && d.SL.rows == 0 && d.mat32;
+// The modes the other compilations fix (see the top of this file): tile streams in the lane-row layout, fp32 slices and
+// fp32 copies of the matrix values in the PCG phases (DevPtrs::mat32), update_info on the streams, plain Jacobi
+// preconditioner; 1 = [A; P] in cluster pairs (kernels_fast.cu), 2 = no pairs (kernels_fast2.cu: one column group, or
+// pairs not available); 0 = none of them, the plain kernels.  Evaluated at every launch, so a workspace that loses its
+// cluster pairs (osqp_abi.cu launch_with_pair_fallback) moves on.
+int fast_mode(const DevPtrs &d, const LaunchGeom &g) {
+  if (!(g.fast && d.blocked && d.SA.lane_rows && (d.m == 0 || d.ST.lane_rows) && d.f32_slices && d.info_streams &&
+        d.W.w == 0 && d.SL.rows == 0 && d.mat32))
+    return 0;
+  if (d.SA.paired) return g.cluster == 2 ? 1 : 0;
+  return g.cluster == 1 ? 2 : 0;
+}
+
+// the cooperative kernels of all compilations (attributes and occupancy are set / taken over all of them)
+int coop_kernel_list(const void **f) {
+  f[0] = (const void *)admm_kernel;
+  f[1] = (const void *)polish_kernel;
+  kernels_fast(&f[2], &f[3]);
+  kernels_fast2(&f[4], &f[5]);
+  return 6;
 }
 
 cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma, cudaStream_t st) {
@@ -2817,8 +2837,11 @@ cudaError_t launch_scatter_values(double *dst, const double *vals, const long lo
 }
 
 cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
-  if (fast_mode(d, g)) return launch_solve_fast(d, cfg, g, st);
-  return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
+  switch (fast_mode(d, g)) {
+    case 1: return launch_solve_fast(d, cfg, g, st);
+    case 2: return launch_solve_fast2(d, cfg, g, st);
+    default: return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
+  }
 }
 
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,
@@ -2899,28 +2922,24 @@ cudaError_t raise_dyn_smem(const void *func, size_t bytes) {
 }
 
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
-  const void *fa = nullptr, *fp = nullptr;
-  fast_kernels(&fa, &fp);
-  cudaError_t e = raise_dyn_smem(fa, dyn_smem);
-  if (e != cudaSuccess) return e;
-  e = raise_dyn_smem(fp, dyn_smem);
-  if (e != cudaSuccess) return e;
-  e = raise_dyn_smem((const void *)admm_kernel, dyn_smem);
-  if (e != cudaSuccess) return e;
-  e = raise_dyn_smem((const void *)spmv_stream_kernel, dyn_smem);
-  if (e != cudaSuccess) return e;
-  return raise_dyn_smem((const void *)polish_kernel, dyn_smem);
+  const void *f[6];
+  const int nf = coop_kernel_list(f);
+  for (int k = 0; k < nf; k++) {
+    cudaError_t e = raise_dyn_smem(f[k], dyn_smem);
+    if (e != cudaSuccess) return e;
+  }
+  return raise_dyn_smem((const void *)spmv_stream_kernel, dyn_smem);
 }
 
 int coop_threads() { return kThreads; }
 
 size_t coop_static_smem() {
-  const void *f[4] = {(const void *)admm_kernel, (const void *)polish_kernel, nullptr, nullptr};
-  fast_kernels(&f[2], &f[3]);
+  const void *f[6];
+  const int nf = coop_kernel_list(f);
   size_t most = 0;
-  for (const void *k : f) {
+  for (int k = 0; k < nf; k++) {
     cudaFuncAttributes a{};
-    if (cudaFuncGetAttributes(&a, k) != cudaSuccess) {
+    if (cudaFuncGetAttributes(&a, f[k]) != cudaSuccess) {
       cudaGetLastError();
       return 16384;
     }
@@ -2930,12 +2949,12 @@ size_t coop_static_smem() {
 }
 
 int max_coop_blocks_per_sm(int block, size_t dyn_smem) {
-  const void *f[4] = {(const void *)admm_kernel, (const void *)polish_kernel, nullptr, nullptr};
-  fast_kernels(&f[2], &f[3]);
+  const void *f[6];
+  const int nf = coop_kernel_list(f);
   int least = 1 << 30;
-  for (const void *k : f) {
+  for (int k = 0; k < nf; k++) {
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, block, dyn_smem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, f[k], block, dyn_smem) != cudaSuccess) return 0;
     least = nb < least ? nb : least;
   }
   return least;
@@ -2953,8 +2972,11 @@ cudaError_t launch_fill_wood(const DevPtrs &d, cudaStream_t st) {
 
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                           cudaStream_t st) {
-  if (fast_mode(d, g)) return launch_polish_fast(d, cfg, sc, out, g, st);
-  return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
+  switch (fast_mode(d, g)) {
+    case 1: return launch_polish_fast(d, cfg, sc, out, g, st);
+    case 2: return launch_polish_fast2(d, cfg, sc, out, g, st);
+    default: return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
+  }
 }
 #endif  // OSQP_B200_FAST
 

@@ -1661,7 +1661,7 @@ static c_int solve_impl(Engine &e) {
 
   CU_OK(cudaEventRecord(e.ev0, e.stream));
   CU_OK(launch_with_pair_fallback(e, [&]() { return launch_solve(e.d, c, e.geom, e.stream); }));
-  e.prof.fast_kernels = fast_mode(e.d, e.geom) ? 1 : 0;
+  e.prof.fast_kernels = fast_mode(e.d, e.geom);
   CU_OK(cudaEventRecord(e.ev1, e.stream));
   e.prof.launches += 1;
   e.wood_dirty = false;  // the launch leaves the Woodbury data consistent with the rho it ends on

@@ -444,14 +444,16 @@ def test_two_models_with_different_slices_coexist(pkg, engine_lib):
     m2.clean()
 
 
-def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
-    # csrc/kernels_fast.cu: the ADMM and polish kernels compiled with the storage mode of the common large sparse
-    # problem fixed (lane rows, cluster pairs, fp32 slices, Jacobi); its PCG phases stream fp32 copies of the matrix
-    # values (DevPtrs::mat32), everything else is the same source.  Both compilations must end at the same termination
-    # check with the same polished point; a workspace that is not in that mode (here: one with the Woodbury
-    # preconditioner switched on by an equality row) must stay on the plain kernels.
+@pytest.mark.parametrize("n,m,density,mode", [(40000, 60000, 0.0008, 1), (12000, 20000, 0.003, 2)])
+def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch, n, m, density, mode):
+    # csrc/kernels_fast.cu, kernels_fast2.cu: the ADMM and polish kernels compiled with the storage mode of the common
+    # large sparse problem fixed (lane rows, fp32 slices, Jacobi; mode 1: [A; P] in cluster pairs, mode 2: no pairs);
+    # their PCG phases stream fp32 copies of the matrix values (DevPtrs::mat32), everything else is the same source.
+    # Both compilations must end at the same termination check with the same polished point; a workspace that is not
+    # in such a mode (here: one with the Woodbury preconditioner switched on by an equality row) must stay on the plain
+    # kernels.
     eng = pkg.load_library(engine_lib)
-    prob = random_qp(40000, 60000, 0.0008, 71)
+    prob = random_qp(n, m, density, 71)
     opts = dict(FIXED_RHO, eps_abs=1e-4, eps_rel=1e-4, check_termination=25, polish=True)
     out = {}
     for fast in (1, 0):
@@ -461,7 +463,7 @@ def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch):
         r = mdl.solve()
         prof = pkg.types.B200Profile()
         assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
-        assert (int(prof.streams), int(prof.paired), int(prof.fast_kernels)) == (1, 1, fast)
+        assert (int(prof.streams), int(prof.paired), int(prof.fast_kernels)) == (1, 1 if mode == 1 else 0, mode * fast)
         out[fast] = r
         mdl.clean()
     a, b = out[1], out[0]
