@@ -274,7 +274,7 @@ cudaError_t launch_cold_start(const DevPtrs &d, cudaStream_t st);
 cudaError_t launch_scatter_values(double *dst, const double *vals, const long long *idx, const int *map,
                                   long long k, cudaStream_t st);
 cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
-// kernels_fast.cu / kernels_fast2.cu: admm_kernel / polish_kernel compiled with the storage mode fixed (kernels.cu fast_mode)
+// kernels_fast.cu / kernels_fast2.cu / kernels_fast3.cu: admm_kernel / polish_kernel compiled with the storage mode fixed (kernels.cu fast_mode)
 int fast_mode(const DevPtrs &d, const LaunchGeom &g);
 cudaError_t launch_solve_fast(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
 cudaError_t launch_polish_fast(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
@@ -284,6 +284,10 @@ cudaError_t launch_solve_fast2(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom
 cudaError_t launch_polish_fast2(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                                 cudaStream_t st);
 void kernels_fast2(const void **admm, const void **polish);
+cudaError_t launch_solve_fast3(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st);
+cudaError_t launch_polish_fast3(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
+                                cudaStream_t st);
+void kernels_fast3(const void **admm, const void **polish);
 cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg &sc, PolishOut *out, LaunchGeom g,
                           cudaStream_t st);
 cudaError_t launch_spmv(const DevPtrs &d, int which, const double *in, double *out, double sigma, LaunchGeom g,

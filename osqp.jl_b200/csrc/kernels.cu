@@ -31,9 +31,11 @@
 #ifdef OSQP_B200_FAST
 #define MODE(x, v) (v)
 #define FAST_PAIRED (OSQP_B200_FAST == 1)  // fixed mode 1: [A; P] in cluster pairs; fixed mode 2 (kernels_fast2.cu): no pairs
+#define FAST_SLACK (OSQP_B200_FAST == 3)   // fixed mode 3 (kernels_fast3.cu): no pairs, slack-elimination preconditioner
 #else
 #define MODE(x, v) (x)
 #define FAST_PAIRED 0
+#define FAST_SLACK 0
 #endif
 
 namespace osqpb200 {
@@ -1113,6 +1115,7 @@ __device__ __noinline__ int pcg_run_stream(Grid &g, RedSmem &sm, Slice &S, Phase
 //   V : w = Pu + sigma u + partials ;  p, s, x, r ;  Ap = t + beta Ap ;  z += alpha Ap ;  |r|inf            | reduce + barrier
 // The [A; P] phase of the preconditioner IS the A phase of the K-apply, so the preconditioner costs one extra A'
 // phase.  Not used by the polish (its penalties are not rho).
+template <bool kM32>
 __device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S, PhaseClock &pc, const DevPtrs &d,
                                                  const PcgVecs &v, const double *rho_vec, const double *Minv, double sigma,
                                                  double *xvec, double *zvec, double rn, double thresh, int max_it, int m0,
@@ -1168,7 +1171,7 @@ __device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S,
     }
     grid_barrier(g);
     // ---- T2
-    stream_phase_f32(S, d.ST, L.g32);
+    stream_phase_f32<kM32>(S, d.ST, L.g32);
     grid_barrier(g);
     // ---- U
     double red[2] = {0.0, 0.0};  // delta, gamma
@@ -1180,31 +1183,31 @@ __device__ __noinline__ int pcg_run_stream_slack(Grid &g, RedSmem &sm, Slice &S,
         red[1] += rj * uj;
       }
     }
-    stream_prefetch_head(d.SA);
+    stream_prefetch_head<kM32>(d.SA);
     grid_barrier(g);
     pc.tick(7);
     // ---- A
     if (MODE(d.SA.paired, FAST_PAIRED)) {
       auto fin = [&](int r, double sum) { finish(r, sum, red[0], red[1]); };
-      stream_phase_paired<true>(S, d.SA, d.uu32, fin);
+      stream_phase_paired<true, kM32>(S, d.SA, d.uu32, fin);
       pc.tick(0);
     } else {
-      stream_phase_f32(S, d.SA, d.uu32);
+      stream_phase_f32<kM32>(S, d.SA, d.uu32);
       pc.tick(0);
       grid_barrier(g);
       pc.tick(1);
       for (int i = m0 + tid; i < m1; i += nth) finish(i, part_sum(d.SA, i), red[0], red[1]);
       for (int j = n0 + tid; j < n1; j += nth) finish(m + j, part_sum(d.SA, m + j), red[0], red[1]);
     }
-    stream_prefetch_head(d.ST);
+    stream_prefetch_head<kM32>(d.ST);
     pc.tick(2);
     reduce_and_barrier<2>(g, sm, red, 0u);
     pc.tick(3);
     const double delta = red[0], gamma = red[1];
     const double beta = (it == 0) ? 0.0 : gamma / gamma_old;
     // ---- B
-    stream_phase_f32(S, d.ST, d.tr32);
-    stream_prefetch_head(d.SA);
+    stream_phase_f32<kM32>(S, d.ST, d.tr32);
+    stream_prefetch_head<kM32>(d.SA);
     pc.tick(4);
     grid_barrier(g);
     pc.tick(5);
@@ -1703,7 +1706,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
   grid_barrier(g);
 
   const bool wood = MODE(d.blocked && d.W.w > 0, false);
-  const bool slack = MODE(d.blocked && d.SL.rows > 0, false);
+  const bool slack = MODE(d.blocked && d.SL.rows > 0, FAST_SLACK);
   if (wood && c.wood_refresh) wood_refresh(g, sm, d, d.rho_vec, c.sigma, d.Minv, n0, n1);
   if (slack && c.wood_refresh) slack_refresh(g, d, d.rho_vec, c.sigma, d.Minv, m0, m1, n0, n1);
 
@@ -1818,7 +1821,7 @@ __global__ void __launch_bounds__(kThreads, 1) admm_kernel(const __grid_constant
       // for no change in parity, and with the Woodbury correction (M = K on the portfolio: one iteration is exact)
       const double ee = c.pcg_eta_e >= 0.0 ? c.pcg_eta_e : (slack ? 1e-3 : 0.0);
       const double tfl = c.pcg_floor * red3[2], ee2 = ee * ee;
-      int ncg = slack     ? pcg_run_stream_slack(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[1],
+      int ncg = slack     ? pcg_run_stream_slack<MODE(false, true)>(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[1],
                                                  thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
                 : MODE(d.blocked, 1) ? pcg_run_stream<MODE(false, true)>(g, sm, SG, pc, d, pv, d.rho_vec, d.Minv, c.sigma, d.xt, d.zt, red3[0],
                                            red3[1], thresh, c.pcg_max_iter, m0, m1, n0, n1, tfl, ee2)
@@ -2734,8 +2737,10 @@ cudaError_t coop_launch(void (*kernel)(Args...), unsigned *bar, LaunchGeom g, cu
 // ------------------------------------------------------------------ host wrappers of the fixed-mode kernels
 #if OSQP_B200_FAST == 1
 #define FASTNAME(x) x##_fast
-#else
+#elif OSQP_B200_FAST == 2
 #define FASTNAME(x) x##_fast2
+#else
+#define FASTNAME(x) x##_fast3
 #endif
 cudaError_t FASTNAME(launch_solve)(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cudaStream_t st) {
   return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
@@ -2751,25 +2756,29 @@ void FASTNAME(kernels)(const void **admm, const void **polish) {
 #else
 // ------------------------------------------------------------------ host wrappers
 // The modes the other compilations fix (see the top of this file): tile streams in the lane-row layout, fp32 slices and
-// fp32 copies of the matrix values in the PCG phases (DevPtrs::mat32), update_info on the streams, plain Jacobi
-// preconditioner; 1 = [A; P] in cluster pairs (kernels_fast.cu), 2 = no pairs (kernels_fast2.cu: one column group, or
-// pairs not available); 0 = none of them, the plain kernels.  Evaluated at every launch, so a workspace that loses its
-// cluster pairs (osqp_abi.cu launch_with_pair_fallback) moves on.
+// fp32 copies of the matrix values in the PCG phases (DevPtrs::mat32), update_info on the streams, no Woodbury rows;
+// 1 = [A; P] in cluster pairs, Jacobi (kernels_fast.cu), 2 = no pairs, Jacobi (kernels_fast2.cu: one column group, or
+// more than two), 3 = no pairs, slack-elimination preconditioner (kernels_fast3.cu); 0 = none of them, the plain
+// kernels.  Evaluated at every launch, so a workspace that loses its cluster pairs (osqp_abi.cu
+// launch_with_pair_fallback) moves on.
 int fast_mode(const DevPtrs &d, const LaunchGeom &g) {
   if (!(g.fast && d.blocked && d.SA.lane_rows && (d.m == 0 || d.ST.lane_rows) && d.f32_slices && d.info_streams &&
-        d.W.w == 0 && d.SL.rows == 0 && d.mat32))
+        d.W.w == 0 && d.mat32))
     return 0;
+  if (d.SL.rows > 0) return (!d.SA.paired && g.cluster == 1) ? 3 : 0;
   if (d.SA.paired) return g.cluster == 2 ? 1 : 0;
   return g.cluster == 1 ? 2 : 0;
 }
 
 // the cooperative kernels of all compilations (attributes and occupancy are set / taken over all of them)
+constexpr int kCoopKernels = 8;
 int coop_kernel_list(const void **f) {
   f[0] = (const void *)admm_kernel;
   f[1] = (const void *)polish_kernel;
   kernels_fast(&f[2], &f[3]);
   kernels_fast2(&f[4], &f[5]);
-  return 6;
+  kernels_fast3(&f[6], &f[7]);
+  return kCoopKernels;
 }
 
 cudaError_t launch_scale_data(const DevPtrs &d, int scaling_iters, double sigma, cudaStream_t st) {
@@ -2840,6 +2849,7 @@ cudaError_t launch_solve(const DevPtrs &d, const SolveCfg &cfg, LaunchGeom g, cu
   switch (fast_mode(d, g)) {
     case 1: return launch_solve_fast(d, cfg, g, st);
     case 2: return launch_solve_fast2(d, cfg, g, st);
+    case 3: return launch_solve_fast3(d, cfg, g, st);
     default: return coop_launch(admm_kernel, d.bar, g, st, d, cfg);
   }
 }
@@ -2922,7 +2932,7 @@ cudaError_t raise_dyn_smem(const void *func, size_t bytes) {
 }
 
 cudaError_t configure_dyn_smem(size_t dyn_smem) {
-  const void *f[6];
+  const void *f[kCoopKernels];
   const int nf = coop_kernel_list(f);
   for (int k = 0; k < nf; k++) {
     cudaError_t e = raise_dyn_smem(f[k], dyn_smem);
@@ -2934,7 +2944,7 @@ cudaError_t configure_dyn_smem(size_t dyn_smem) {
 int coop_threads() { return kThreads; }
 
 size_t coop_static_smem() {
-  const void *f[6];
+  const void *f[kCoopKernels];
   const int nf = coop_kernel_list(f);
   size_t most = 0;
   for (int k = 0; k < nf; k++) {
@@ -2949,7 +2959,7 @@ size_t coop_static_smem() {
 }
 
 int max_coop_blocks_per_sm(int block, size_t dyn_smem) {
-  const void *f[6];
+  const void *f[kCoopKernels];
   const int nf = coop_kernel_list(f);
   int least = 1 << 30;
   for (int k = 0; k < nf; k++) {
@@ -2975,6 +2985,7 @@ cudaError_t launch_polish(const DevPtrs &d, const PolishCfg &cfg, const SolveCfg
   switch (fast_mode(d, g)) {
     case 1: return launch_polish_fast(d, cfg, sc, out, g, st);
     case 2: return launch_polish_fast2(d, cfg, sc, out, g, st);
+    case 3: return launch_polish_fast3(d, cfg, sc, out, g, st);
     default: return coop_launch(polish_kernel, d.bar, g, st, d, cfg, sc, out);
   }
 }
