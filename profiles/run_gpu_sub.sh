@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-(timeout 900 python -m pytest tests/test_configs.py -m gpu -q 2>&1 | tail -12)
-(timeout 600 python bench.py --config 3 --steps 3 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err); tail -c 1800 gpurun_out/bench_c3.json; tail -3 gpurun_out/bench_c3.err
+(OSQP_B200_PAIRS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_final.csv python bench.py --steps 2 --warmup 1 --no-extras --cpu-iters 5 > gpurun_out/r2_bench_under_ncu.log 2>&1); wc -l gpurun_out/r2_launches_final.csv
+(OSQP_B200_PAIRS=0 timeout 900 ncu --set full --clock-control none -k regex:admm_kernel -c 1 -o gpurun_out/admm_full2 python profiles/profile_driver.py --solves 1 --spmv-reps 1 2>&1 | tail -2)
+ls -la gpurun_out/
