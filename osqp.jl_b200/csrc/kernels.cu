@@ -22,12 +22,13 @@
 #include <type_traits>
 #include <utility>
 
-// This file is compiled TWICE.  The plain compilation holds every kernel and decides the storage mode of a workspace
-// at run time (CSR or tile streams, scan or lane-row layout, cluster pairs or not, fp64 or fp32 slices, Jacobi /
-// Woodbury / slack-elimination preconditioner).  kernels_fast.cu includes it again with OSQP_B200_FAST defined: the
-// same admm_kernel / polish_kernel with the mode of the common large sparse problem (fast_mode() below) fixed at
-// compile time.  Less than half the code and fewer spills: measured 5 % faster on every phase of config 2
-// (profiles/r2_ncu_admm.md section 5).  MODE(x, v) is x in the plain compilation and the constant v in the fast one.
+// This file is compiled FOUR times.  The plain compilation holds every kernel and decides the storage mode of a
+// workspace at run time (CSR or tile streams, scan or lane-row layout, cluster pairs or not, fp64 or fp32 slices,
+// Jacobi / Woodbury / slack-elimination preconditioner).  kernels_fast.cu, kernels_fast2.cu and kernels_fast3.cu
+// include it again with OSQP_B200_FAST = 1, 2, 3: the same admm_kernel / polish_kernel with one common mode
+// (fast_mode() below) fixed at compile time.  Less than half the code and fewer spills: measured 5 % faster on every
+// phase of config 2 (profiles/r2_ncu_admm.md section 5).  MODE(x, v) is x in the plain compilation and the constant v
+// in the fixed-mode ones; only those stream fp32 copies of the matrix values in their PCG phases (DevPtrs::mat32).
 #ifdef OSQP_B200_FAST
 #define MODE(x, v) (v)
 #define FAST_PAIRED (OSQP_B200_FAST == 1)  // fixed mode 1: [A; P] in cluster pairs; fixed mode 2 (kernels_fast2.cu): no pairs
