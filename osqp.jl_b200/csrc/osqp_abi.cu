@@ -1123,6 +1123,15 @@ c_int osqp_cleanup(OSQPWorkspace *work) {  // src/interface.jl:224-229 -- NULL a
   return 0;
 }
 
+// The fp32 copies of the matrix values (DevPtrs::mat32) hold SCALED entries: Ruiz scaling multiplies an entry by at most
+// 1e4 * 1e4 (the clamp on D, E) and the cost by at most 1e4 more, so raw entries below 1e25 stay far inside the fp32
+// range.  Data beyond that (nothing a QP solver with OSQP_INFTY = 1e30 is meant for) keeps fp64 values everywhere.
+static bool fits_fp32_copy(const c_float *x, long long k) {
+  for (long long t = 0; t < k; t++)
+    if (!(std::fabs(x[t]) < 1e25)) return false;
+  return true;
+}
+
 c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings *settings) {
   if (workp) *workp = nullptr;
   if (!workp) return 1;
@@ -1527,7 +1536,8 @@ c_int osqp_setup(OSQPWorkspace **workp, const OSQPData *data, const OSQPSettings
 
   // fp32 copies of the stream values for the PCG phases of the fixed-mode kernels (engine.cuh DevPtrs::mat32)
   d.mat32 = 0;
-  if (env_int("OSQP_B200_MAT32", 1) != 0) {
+  if (env_int("OSQP_B200_MAT32", 1) != 0 && fits_fp32_copy(data->P->x, data->P->p[data->n]) &&
+      fits_fp32_copy(data->A->x, data->A->p[data->n])) {
     d.mat32 = 1;  // provisional: fast_mode() looks at it
     if (fast_mode(d, e.geom)) {
       CU_OK(dalloc(e, &d.SA.val32, (size_t)d.SA.nelem + 8));
@@ -1888,6 +1898,9 @@ static c_int update_PA(Engine &e, const c_float *Px_new, const c_int *Px_idx, c_
             (long long)A_n, (long long)e.nnzA);
     return doP ? 2 : 1;
   }
+  if (e.d.mat32 && ((doP && !fits_fp32_copy(Px_new, Px_idx ? P_n : e.nnzPtriu)) ||
+                    (doA && !fits_fp32_copy(Ax_new, Ax_idx ? A_n : e.nnzA))))
+    e.d.mat32 = 0;  // from now on the plain kernels (kernels.cu fast_mode)
   if (doP) {
     const long long k = Px_idx ? P_n : e.nnzPtriu;
     if (Px_idx)
