@@ -496,6 +496,18 @@ def test_fixed_mode_kernels_match_plain_kernels(pkg, engine_lib, monkeypatch, n,
     assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0
     assert r.info.status == "Solved" and int(prof.streams) == 1 and int(prof.fast_kernels) == 0
     mdl.clean()
+    # an entry outside the range that is safe for the fp32 copies (after scaling): fp64 values, plain kernels -- at setup
+    # and when it arrives through osqp_update_A
+    mdl = pkg.Model(lib=engine_lib)
+    mdl.setup(**prob, **dict(opts, polish=False, max_iter=2))
+    mdl.solve()
+    assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0 and int(prof.fast_kernels) == mode
+    Ax = prob["A"].tocsc().data.copy()
+    Ax[0] = 1e26
+    mdl.update(Ax=Ax)
+    mdl.solve()
+    assert eng.osqp_b200_get_profile(mdl.workspace, C.byref(prof)) == 0 and int(prof.fast_kernels) == 0
+    mdl.clean()
 
 
 def test_tiny_mode_settings_variants_match_oracle(pkg, engine_lib, oracle_lib):
